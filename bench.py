@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: Mpixels/s, Canny+HoughKHT @1080p; % HBM roofline; vs ref AVX2 CPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic 1920x1080 frames (BASELINE.json configs[1]):
+Gaussian 5x5 (sigma 1) -> Canny (Sobel 3x3, tLow 59, tHigh 119) per frame.  Frames are sharded across ranks with no
+data-path collective (weak scaling: every rank owns `--frames` frames).
+
+  value : whole-job Mpixels/s with the frames already resident in HBM (device API, CUDA events, max over ranks)
+  e2e   : the same metric through the reference-facing host call (cvb200_edge_dete_process_batch): pinned host frames in,
+          host edge maps out, H2D and D2H inside the timed region
+  roofline / cpu_baseline : see DESIGN.md section "Measurement"
+
+--impl reference times the UNMODIFIED reference (oracle/_ref, AVX2 intrinsics, all host threads) on the same config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+W, H = 1920, 1080
+TLOW, THIGH, KS = 59.0, 119.0, 3
+BLUR, SIGMA = 5, 1.0
+ALG_BYTES_PER_PX = 2.0  # 1 B/px read (frame) + 1 B/px written (edge map); blur and gradients stay on chip
+METRIC = "Mpixels/s Canny (Gaussian5x5+Sobel+NMS+hysteresis) @1080p"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def make_frames(n, seed0):
+    from frames import frame_g
+    return np.stack([frame_g(W, H, seed0 + k) for k in range(n)])
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the unmodified reference (oracle/_ref) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import oracle
+    cores = os.cpu_count() or 1
+    frames_per_step = max(1, min(args.frames, 8))  # bounded sample of the workload per step
+    frames = make_frames(frames_per_step, 12345)
+    r = oracle.ref(-1)
+    threads = r.ref_threads_count()
+    sess = oracle.RefEdgeSession(frames, "canny", TLOW, THIGH, KS, BLUR, SIGMA, threads=-1)
+
+    def step():
+        return sess.run(0, frames_per_step)[0]
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    mpx = frames_per_step * args.steps * W * H / 1e6
+    value = mpx / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16 (+f32 blur)",
+        "data": "synthetic", "config": {"workload": "gauss5x5+canny_1080p", "width": W, "height": H, "frames_per_step": frames_per_step,
+                                         "tLow": TLOW, "tHigh": THIGH, "kernSize": KS, "blur": [BLUR, SIGMA]},
+        "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": threads, "kind": "reference",
+                         "sample": "%d frames/step x %d steps, CompV reference AVX2 intrinsics (asm disabled), %d pool threads on %d host cores" % (frames_per_step, args.steps, threads, cores)},
+        "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per rank per step")
+    ap.add_argument("--cpu-frames", type=int, default=400, help="frames timed for cpu_baseline (rank 0, N=1)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import compv_b200 as cvb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU reference)")
+    torch.cuda.set_device(local_rank)
+    cvb.init(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.frames
+    frames = make_frames(B, 12345 + rank * 1000)                  # (B, H, W) uint8, 133 MB for B=64: larger than the 126 MB L2
+    h_in = torch.from_numpy(frames).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    d_in = h_in.cuda()
+    d_out = torch.empty_like(d_in)
+    dete = cvb.CompVEdgeDete.newObj(cvb.CANNY_ID, TLOW, THIGH, KS)
+    dete.set_preblur(BLUR, SIGMA)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        dete.process_dev(d_in, W, H, W, d_out, batch=B, stream=stream)
+
+    def step_e2e():
+        dete.process_batch(h_in.numpy(), width=W, edges=h_out.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        dev = e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([dev, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = cvb.launch_count()
+    dev_ms, _ = timed(step_dev, args.steps)
+    launches = cvb.launch_count() - l0
+    # ---- end to end through the host call (H2D + D2H inside) ----
+    for _ in range(2):
+        step_e2e()
+    _, e2e_ms = timed(step_e2e, args.steps)   # the host call is synchronous: wall clock around it is the honest number
+    clocks = sampler.stop() if rank == 0 else None
+
+    px_per_step = B * W * H * world
+    value = px_per_step * args.steps / (dev_ms * 1e-3) / 1e6
+    e2e_value = px_per_step * args.steps / (e2e_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA-event timing over extra steps (rank 0) ----
+    roof, kernels = None, {}
+    if rank == 0:
+        cvb.lib().cvb200_profile_begin()
+        psteps = min(args.steps, 10)
+        for _ in range(psteps):
+            step_dev()
+        buf = C.create_string_buffer(1 << 16)
+        cvb.check(cvb.lib().cvb200_profile_end(buf, C.c_size_t(len(buf))), "cvb200_profile_end")
+        for ln in buf.value.decode().splitlines():
+            name, cnt, ms = ln.split()
+            kernels[name] = {"launches": int(cnt), "total_ms": float(ms), "avg_ms": float(ms) / max(int(cnt), 1)}
+        step_ms = sum(k["total_ms"] for k in kernels.values()) / psteps
+        top = max(kernels, key=lambda n: kernels[n]["total_ms"])
+        for k in kernels.values():
+            k["share"] = k["total_ms"] / psteps / step_ms
+        peak, how = load_peaks()
+        alg_bytes = ALG_BYTES_PER_PX * B * W * H  # one launch of canny_front processes the whole batch
+        achieved = alg_bytes / (kernels[top]["avg_ms"] * 1e-3) / 1e9 if top == "canny_front" else \
+            alg_bytes / (kernels["canny_front"]["avg_ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "canny_front", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": how, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": kernels["canny_front"]["avg_ms"],
+                "top_kernel_by_time": top}
+
+    # ---- CPU baseline: the compiled reference on this host's cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        try:
+            import oracle
+            r = oracle.ref(-1)
+            n = max(1, args.cpu_frames)
+            sess = oracle.RefEdgeSession(frames[:8], "canny", TLOW, THIGH, KS, BLUR, SIGMA, threads=-1)
+            sess.run(0, 8)  # warm-up
+            ms, _ = sess.run(0, n)
+            cpu = {"value": n * W * H / 1e6 / (ms * 1e-3), "unit": "Mpixels/s", "cores": int(r.ref_threads_count()), "kind": "reference",
+                   "sample": "%d x 1080p frames (Gaussian5x5 + Canny, 8 distinct frames cycled), CompV reference, AVX2 intrinsics, asm disabled, %.3f ms/frame, %d host cores" % (n, ms / n, os.cpu_count())}
+        except Exception as ex:  # the bench line must still come out
+            cpu = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int16 (+f32 blur)", "data": "synthetic",
+            "config": {"workload": "gauss5x5+canny_1080p", "width": W, "height": H, "frames_per_gpu_per_step": B, "tLow": TLOW, "tHigh": THIGH,
+                       "kernSize": KS, "blur": [BLUR, SIGMA], "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6),
+                       "parallelism": "frames sharded across %d GPU(s), no collective" % world},
+            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": B * W * H * world, "d2h_bytes_per_step": B * W * H * world,
+                    "ms_per_step": e2e_ms / args.steps, "api": "cvb200_edge_dete_process_batch (pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+"""compv_b200 -- B200-native (sm_100a) implementation of CompV's per-pixel image hot path.
+
+The product is `lib/libcompv_b200.so` (hand-written CUDA kernels behind the C ABI of include/cvb200.h).  This Python
+package is the harness-side binding used by tests/ and bench.py: numpy in, numpy out, every call goes through the
+C ABI.  Class and method names mirror the reference's C++ API (CompVEdgeDete::newObj / process, CompVMathConvlt::convlt1 ...)
+so that the parity tests read like the reference's own tests.  There is no CPU fallback: a missing library or a missing
+GPU raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import (CvbError, lib, check, vp, sz,  # noqa: F401
+                   SOBEL_ID, SCHARR_ID, PREWITT_ID, CANNY_ID, FAST_ID, HOUGHSHT_ID, HOUGHKHT_ID, HOGS_ID, PLSL_ID, LMSER_ID,
+                   BORDER_TYPE_ZERO, BORDER_TYPE_IGNORE, BORDER_TYPE_REPLICATE)
+
+_initialised_device = None
+
+CONV_TYPES = {
+    "8u16s16s": (np.uint8, np.int16, np.int16),
+    "16s16s16s": (np.int16, np.int16, np.int16),
+    "8u32f8u": (np.uint8, np.float32, np.uint8),
+    "8u32f32f": (np.uint8, np.float32, np.float32),
+    "32f32f32f": (np.float32, np.float32, np.float32),
+    "32f32f8u": (np.float32, np.float32, np.uint8),
+    "fxp_8u16u8u": (np.uint8, np.uint16, np.uint8),
+}
+
+
+def init(device=0):
+    """cvb200_init: bind to a CUDA device (replaces CompVGpu::init, gpu/compv_gpu.cxx:36-62)."""
+    global _initialised_device
+    if _initialised_device != device:
+        check(lib().cvb200_init(int(device)), "cvb200_init")
+        _initialised_device = device
+
+
+def launch_count():
+    return int(lib().cvb200_launch_count())
+
+
+def _frame(img, width):
+    assert img.ndim == 2 and img.flags.c_contiguous, "frames are (height, stride) C-contiguous arrays"
+    h, stride = img.shape
+    return (stride if width is None else int(width)), h, stride
+
+
+# ---- a2: CompVMathConvlt ---------------------------------------------------------------------------
+def convlt1(name, img, vt_kern, hz_kern, width=None, border=BORDER_TYPE_ZERO, out=None):
+    """CompVMathConvlt::convlt1<In,Kern,Out> / convlt1FixedPoint on host buffers.  Returns the (height, stride) output plane."""
+    tin, tk, tout = CONV_TYPES[name]
+    assert img.dtype == tin
+    vt = np.ascontiguousarray(vt_kern, dtype=tk)
+    hz = np.ascontiguousarray(hz_kern, dtype=tk)
+    assert len(vt) == len(hz)
+    w, h, stride = _frame(img, width)
+    if out is None:
+        out = np.zeros((h, stride), dtype=tout)
+    fn = getattr(lib(), "cvb200_convlt1_" + name)
+    check(fn(vp(img), sz(w), sz(h), sz(stride), vp(vt), vp(hz), sz(len(vt)), vp(out), int(border)), "cvb200_convlt1_" + name)
+    return out
+
+
+def gauss_kernel(size, sigma, fixed_point=False):
+    """CompVMathGauss::kernelDim1<float> / kernelDim1FixedPoint."""
+    k = np.zeros(size, dtype=np.uint16 if fixed_point else np.float32)
+    fn = lib().cvb200_gauss_kernel_dim1_fxp if fixed_point else lib().cvb200_gauss_kernel_dim1_32f
+    check(fn(sz(size), C.c_float(sigma), vp(k)), "cvb200_gauss_kernel_dim1")
+    return k
+
+
+def sobel_g(img, kind_id=SOBEL_ID, ks=3, width=None):
+    """gx, gy (int16) and g = |gx|+|gy| (uint16): convlt1<u8,int16,int16> x2 + CompVMathUtils::sumAbs."""
+    w, h, stride = _frame(img, width)
+    gx = np.zeros((h, stride), np.int16)
+    gy = np.zeros((h, stride), np.int16)
+    g = np.zeros((h, stride), np.uint16)
+    check(lib().cvb200_sobel_g(vp(img), sz(w), sz(h), sz(stride), int(kind_id), sz(ks), vp(gx), vp(gy), vp(g)), "cvb200_sobel_g")
+    return gx, gy, g
+
+
+# ---- a3 / a5: CompVEdgeDete ------------------------------------------------------------------------
+class CompVEdgeDete:
+    """Mirror of CompVEdgeDete (base/include/compv/base/compv_features.h:205-215) over cvb200_edge_dete_*."""
+
+    EDGE_SET_BOOL_X86_SSE41_GMAX_LANES = 1000
+
+    def __init__(self, handle, dete_id):
+        self._h = handle
+        self.id = dete_id
+
+    @staticmethod
+    def newObj(dete_id, tLow=0.8, tHigh=1.6, kernSize=3):
+        h = C.c_void_p()
+        check(lib().cvb200_edge_dete_new(C.byref(h), int(dete_id), C.c_float(tLow), C.c_float(tHigh), sz(kernSize)), "cvb200_edge_dete_new")
+        return CompVEdgeDete(h, dete_id)
+
+    def set(self, cap_id, value, ctype):
+        v = ctype(value)
+        return lib().cvb200_edge_dete_set(self._h, int(cap_id), C.byref(v), sz(C.sizeof(v)))
+
+    def setInt(self, cap_id, value):
+        check(self.set(cap_id, value, C.c_int32), "cvb200_edge_dete_set")
+
+    def setFloat32(self, cap_id, value):
+        check(self.set(cap_id, value, C.c_float), "cvb200_edge_dete_set")
+
+    def setBool(self, cap_id, value):
+        check(self.set(cap_id, bool(value), C.c_bool), "cvb200_edge_dete_set")
+
+    def set_preblur(self, size, sigma):
+        check(lib().cvb200_edge_dete_set_preblur(self._h, sz(size), C.c_float(sigma)), "cvb200_edge_dete_set_preblur")
+
+    def process(self, image, width=None, edges=None):
+        """Host buffers in, host buffers out (H2D + kernels + D2H inside the call)."""
+        w, h, stride = _frame(image, width)
+        if edges is None:
+            edges = np.zeros((h, stride), np.uint8)
+        check(lib().cvb200_edge_dete_process(self._h, vp(image), sz(w), sz(h), sz(stride), vp(edges)), "cvb200_edge_dete_process")
+        return edges
+
+    def process_batch(self, images, width=None, edges=None):
+        """(batch, height, stride) host array (ideally pinned) -> same-shape edge maps; pipelined H2D/compute/D2H inside the call."""
+        assert images.ndim == 3 and images.flags.c_contiguous
+        b, h, stride = images.shape
+        w = stride if width is None else int(width)
+        if edges is None:
+            edges = np.zeros_like(images)
+        check(lib().cvb200_edge_dete_process_batch(self._h, vp(images), sz(w), sz(h), sz(stride), vp(edges), sz(b), sz(h * stride)), "cvb200_edge_dete_process_batch")
+        return edges
+
+    def process_dev(self, d_image, width, height, stride, d_edges, batch=1, frame_pitch=0, stream=0):
+        """Device pointers (ints or torch tensors), batched, on `stream` (a cudaStream_t value)."""
+        check(lib().cvb200_edge_dete_process_dev(self._h, vp(d_image), sz(width), sz(height), sz(stride), vp(d_edges), sz(batch), sz(frame_pitch),
+                                                 C.c_void_p(stream)), "cvb200_edge_dete_process_dev")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cvb200_edge_dete_free(C.byref(self._h))
+        except Exception:
+            pass

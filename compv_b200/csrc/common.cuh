@@ -1,0 +1,77 @@
+// Shared device/host helpers for libcompv_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <atomic>
+#include <mutex>
+
+#include "../../include/cvb200.h"
+
+namespace cvb {
+
+// ---- runtime state (runtime.cu) ----
+extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_device;          // -1 when not initialised
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int num_sms();
+
+#define CVB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return ::cvb::cuda_fail(e__, #x, __FILE__, __LINE__); } while (0)
+#define CVB_CHECK(x) do { int c__ = (x); if (c__ != CVB200_S_OK) return c__; } while (0)
+#define CVB_REQUIRE(cond, code) do { if (!(cond)) return (code); } while (0)
+#define CVB_REQUIRE_INIT() do { if (::cvb::g_device.load() < 0) return CVB200_E_NOT_INITIALIZED; } while (0)
+// call after every kernel launch: counts it and surfaces launch-configuration errors immediately
+#define CVB_LAUNCHED() do { ::cvb::g_launches.fetch_add(1, std::memory_order_relaxed); CVB_CUDA(cudaGetLastError()); } while (0)
+
+static inline cudaStream_t as_stream(cvb200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Per-kernel device timing (cvb200_profile_begin/_end): when enabled, every launch site brackets its kernel with CUDA events on the
+// launching stream.  Disabled (the default) it costs one relaxed atomic load per launch.
+extern std::atomic<int> g_profiling;
+void profile_mark(const char* name, cudaStream_t stream, bool begin);
+struct KernelScope {
+	const char* name; cudaStream_t stream; bool on;
+	KernelScope(const char* n, cudaStream_t s) : name(n), stream(s), on(g_profiling.load(std::memory_order_relaxed) != 0) { if (on) profile_mark(name, stream, true); }
+	~KernelScope() { if (on) profile_mark(name, stream, false); }
+};
+
+// Grow-only device scratch buffer (the reference caches its scratch per object the same way, e.g. canny_dete.cxx:133-147)
+struct DevBuf {
+	void* p = nullptr;
+	size_t bytes = 0;
+	int ensure(size_t n) {
+		if (n <= bytes && p) return CVB200_S_OK;
+		if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+		if (n == 0) n = 256;
+		cudaError_t e = cudaMalloc(&p, n);
+		if (e != cudaSuccess) { p = nullptr; return e == cudaErrorMemoryAllocation ? (cudaGetLastError(), CVB200_E_OUT_OF_MEMORY) : cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+		bytes = n;
+		return CVB200_S_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+	template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Pinned host scratch (for small read-backs: flags, counts, thresholds)
+struct HostBuf {
+	void* p = nullptr;
+	size_t bytes = 0;
+	int ensure(size_t n) {
+		if (n <= bytes && p) return CVB200_S_OK;
+		if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+		cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+		if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__); }
+		bytes = n;
+		return CVB200_S_OK;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+	template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ----
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+} // namespace cvb

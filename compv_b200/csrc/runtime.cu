@@ -1,0 +1,238 @@
+// Runtime plumbing of libcompv_b200.so: device binding, error strings, memory/stream helpers.
+// Replaces the reference's CompVGpu::init probe (gpu/compv_gpu.cxx:36-62), which only dlopen()s libcuda and sets a flag.
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+
+namespace cvb {
+
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_device{-1};
+static int g_num_sms = 0;
+static thread_local std::string t_last_cuda_error;
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+	char buf[512];
+	snprintf(buf, sizeof(buf), "%s: %s (%s:%d)", cudaGetErrorName(e), what, file, line);
+	t_last_cuda_error = buf;
+	cudaGetLastError(); // clear sticky-less errors so that the next call starts clean
+	return e == cudaErrorMemoryAllocation ? CVB200_E_OUT_OF_MEMORY : CVB200_E_CUDA;
+}
+
+int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+// ---- per-kernel timing ----
+std::atomic<int> g_profiling{0};
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mutex;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event()
+{
+	if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	return e;
+}
+
+void profile_mark(const char* name, cudaStream_t stream, bool begin)
+{
+	std::lock_guard<std::mutex> lock(g_prof_mutex);
+	if (begin) {
+		ProfRec r; r.name = name; r.e0 = prof_event(); r.e1 = nullptr;
+		cudaEventRecord(r.e0, stream);
+		g_prof_recs.push_back(r);
+	}
+	else {
+		for (size_t i = g_prof_recs.size(); i-- > 0;) {
+			if (g_prof_recs[i].name == name && !g_prof_recs[i].e1) {
+				g_prof_recs[i].e1 = prof_event();
+				cudaEventRecord(g_prof_recs[i].e1, stream);
+				break;
+			}
+		}
+	}
+}
+
+} // namespace cvb
+
+using namespace cvb;
+
+extern "C" {
+
+int cvb200_init(int device)
+{
+	CVB_REQUIRE(device >= 0, CVB200_E_INVALID_PARAMETER);
+	int count = 0;
+	CVB_CUDA(cudaGetDeviceCount(&count));
+	CVB_REQUIRE(device < count, CVB200_E_INVALID_PARAMETER);
+	CVB_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CVB_CUDA(cudaGetDeviceProperties(&prop, device));
+	// sm_100a cubins only: there is deliberately no PTX/other-arch fallback in this library
+	if (prop.major != 10) {
+		char buf[256];
+		snprintf(buf, sizeof(buf), "device %d is sm_%d%d; libcompv_b200 is built for sm_100a only", device, prop.major, prop.minor);
+		// stored through cuda_fail's thread-local so that cvb200_last_cuda_error() explains the refusal
+		cvb::cuda_fail(cudaErrorNoKernelImageForDevice, buf, __FILE__, __LINE__);
+		return CVB200_E_CUDA;
+	}
+	g_num_sms = prop.multiProcessorCount;
+	CVB_CUDA(cudaFree(0)); // force primary-context creation
+	g_device.store(device);
+	return CVB200_S_OK;
+}
+
+int cvb200_deinit(void)
+{
+	g_device.store(-1);
+	return CVB200_S_OK;
+}
+
+int cvb200_is_active(void) { return g_device.load() >= 0 ? 1 : 0; }
+
+int cvb200_device_count(int* count)
+{
+	CVB_REQUIRE(count, CVB200_E_INVALID_PARAMETER);
+	*count = 0;
+	CVB_CUDA(cudaGetDeviceCount(count));
+	return CVB200_S_OK;
+}
+
+const char* cvb200_error_string(int code)
+{
+	switch (code) {
+	case CVB200_S_OK: return "S_OK";
+	case CVB200_E_NOT_IMPLEMENTED: return "E_NOT_IMPLEMENTED";
+	case CVB200_E_NOT_INITIALIZED: return "E_NOT_INITIALIZED";
+	case CVB200_E_INVALID_CALL: return "E_INVALID_CALL";
+	case CVB200_E_INVALID_STATE: return "E_INVALID_STATE";
+	case CVB200_E_INVALID_PARAMETER: return "E_INVALID_PARAMETER";
+	case CVB200_E_INVALID_SUBTYPE: return "E_INVALID_SUBTYPE";
+	case CVB200_E_OUT_OF_MEMORY: return "E_OUT_OF_MEMORY";
+	case CVB200_E_OUT_OF_BOUND: return "E_OUT_OF_BOUND";
+	case CVB200_E_MEMORY_NOT_ALIGNED: return "E_MEMORY_NOT_ALIGNED";
+	case CVB200_E_CUDA: return "E_CUDA";
+	default: return "E_UNKNOWN";
+	}
+}
+
+const char* cvb200_last_cuda_error(void) { return t_last_cuda_error.c_str(); }
+
+uint64_t cvb200_launch_count(void) { return g_launches.load(); }
+
+int cvb200_profile_begin(void)
+{
+	CVB_REQUIRE_INIT();
+	g_profiling.store(1);
+	return CVB200_S_OK;
+}
+
+// Writes "name count total_ms\n" lines (one per kernel name) into buf; stops profiling and recycles the events.
+int cvb200_profile_end(char* buf, size_t bufSize)
+{
+	CVB_REQUIRE(buf && bufSize, CVB200_E_INVALID_PARAMETER);
+	g_profiling.store(0);
+	CVB_CUDA(cudaDeviceSynchronize());
+	std::lock_guard<std::mutex> lock(g_prof_mutex);
+	std::map<std::string, std::pair<uint64_t, double> > acc;
+	for (auto& r : g_prof_recs) {
+		if (r.e0 && r.e1) {
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { auto& a = acc[r.name]; a.first += 1; a.second += ms; }
+		}
+		if (r.e0) g_prof_pool.push_back(r.e0);
+		if (r.e1) g_prof_pool.push_back(r.e1);
+	}
+	g_prof_recs.clear();
+	std::string out;
+	char line[256];
+	for (auto& kv : acc) {
+		snprintf(line, sizeof(line), "%s %llu %.6f\n", kv.first.c_str(), static_cast<unsigned long long>(kv.second.first), kv.second.second);
+		out += line;
+	}
+	CVB_REQUIRE(out.size() + 1 <= bufSize, CVB200_E_OUT_OF_BOUND);
+	memcpy(buf, out.c_str(), out.size() + 1);
+	return CVB200_S_OK;
+}
+
+int cvb200_malloc(void** dptr, size_t bytes)
+{
+	CVB_REQUIRE(dptr, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE_INIT();
+	*dptr = nullptr;
+	CVB_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+	return CVB200_S_OK;
+}
+
+int cvb200_free(void* dptr)
+{
+	if (dptr) CVB_CUDA(cudaFree(dptr));
+	return CVB200_S_OK;
+}
+
+int cvb200_host_alloc(void** hptr, size_t bytes)
+{
+	CVB_REQUIRE(hptr, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE_INIT();
+	*hptr = nullptr;
+	CVB_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+	return CVB200_S_OK;
+}
+
+int cvb200_host_free(void* hptr)
+{
+	if (hptr) CVB_CUDA(cudaFreeHost(hptr));
+	return CVB200_S_OK;
+}
+
+int cvb200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, cvb200_stream_t stream)
+{
+	CVB_REQUIRE(dptr && hptr, CVB200_E_INVALID_PARAMETER);
+	CVB_CUDA(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+	return CVB200_S_OK;
+}
+
+int cvb200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, cvb200_stream_t stream)
+{
+	CVB_REQUIRE(dptr && hptr, CVB200_E_INVALID_PARAMETER);
+	CVB_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+	return CVB200_S_OK;
+}
+
+int cvb200_memset(void* dptr, int value, size_t bytes, cvb200_stream_t stream)
+{
+	CVB_REQUIRE(dptr, CVB200_E_INVALID_PARAMETER);
+	CVB_CUDA(cudaMemsetAsync(dptr, value, bytes, as_stream(stream)));
+	return CVB200_S_OK;
+}
+
+int cvb200_stream_create(cvb200_stream_t* stream)
+{
+	CVB_REQUIRE(stream, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE_INIT();
+	cudaStream_t s;
+	CVB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	*stream = reinterpret_cast<cvb200_stream_t>(s);
+	return CVB200_S_OK;
+}
+
+int cvb200_stream_destroy(cvb200_stream_t stream)
+{
+	if (stream) CVB_CUDA(cudaStreamDestroy(as_stream(stream)));
+	return CVB200_S_OK;
+}
+
+int cvb200_stream_sync(cvb200_stream_t stream)
+{
+	CVB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+	return CVB200_S_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,192 @@
+/*
+ * cvb200.h -- C ABI of libcompv_b200.so: the B200-native (sm_100a) implementation of CompV's per-pixel hot path.
+ *
+ * Conventions (they mirror the reference so that a CompV maintainer can bind these 1:1):
+ *   - every function returns an int that is a COMPV_ERROR_CODE numeric value
+ *     (reference: base/include/compv/base/compv_common.h:226-279): 0 = S_OK, >= 20000 = error.
+ *   - images are single-plane, row-major; `stride` is in SAMPLES (not bytes), exactly like CompVMat::stride()
+ *     (reference: base/include/compv/base/compv_mat.h:21-588).
+ *   - functions without suffix take caller-owned HOST buffers (the shape of the reference's dormant GPU hook
+ *     CompVGpuCornerDeteFAST::processData, gpu/include/compv/gpu/core/features/fast/compv_gpu_feature_fast_dete.h:23-47)
+ *     and perform H2D / kernels / D2H internally, synchronously.
+ *   - functions with the `_dev` suffix take DEVICE pointers, a batch of `batch` frames spaced `framePitch` samples apart
+ *     (0 -> stride*height) and a cudaStream_t passed as void*; they are asynchronous with respect to the host unless noted.
+ *   - setters/getters use the reference's CompVCaps convention set(id, valuePtr, valueSize)
+ *     (base/include/compv/base/compv_caps.h:15-35) with the same ids and the same size checks.
+ *   - no function falls back to a CPU implementation: if CUDA is unavailable the call returns CVB200_E_CUDA.
+ */
+#ifndef CVB200_H_
+#define CVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#  define CVB200_API __attribute__((visibility("default")))
+#else
+#  define CVB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes: numeric values of COMPV_ERROR_CODE (compv_common.h:226-279) ---- */
+#define CVB200_S_OK                    0
+#define CVB200_E_NOT_IMPLEMENTED       20001
+#define CVB200_E_NOT_INITIALIZED       20002
+#define CVB200_E_INVALID_CALL          20004
+#define CVB200_E_INVALID_STATE         20005
+#define CVB200_E_INVALID_PARAMETER     20006
+#define CVB200_E_INVALID_SUBTYPE       20009
+#define CVB200_E_OUT_OF_MEMORY         20013
+#define CVB200_E_OUT_OF_BOUND          20014
+#define CVB200_E_MEMORY_NOT_ALIGNED    20021
+#define CVB200_E_CUDA                  20035
+
+/* ---- feature ids and capability ids: numeric values of the anonymous enum in
+ *      base/include/compv/base/compv_features.h:47-121 and base/include/compv/base/compv_ccl.h:61-103 ---- */
+#define CVB200_FAST_ID                                  1
+#define CVB200_FAST_SET_INT_THRESHOLD                   2
+#define CVB200_FAST_SET_INT_MAX_FEATURES                3
+#define CVB200_FAST_SET_INT_FAST_TYPE                   4
+#define CVB200_FAST_SET_BOOL_NON_MAXIMA_SUPP            5
+#define CVB200_FAST_TYPE_9                              6
+#define CVB200_FAST_TYPE_12                             7
+#define CVB200_CANNY_ID                                 20
+#define CVB200_CANNY_SET_INT_KERNEL_SIZE                21
+#define CVB200_CANNY_SET_INT_THRESHOLD_TYPE             22
+#define CVB200_CANNY_SET_FLT32_THRESHOLD_LOW            23
+#define CVB200_CANNY_SET_FLT32_THRESHOLD_HIGH           24
+#define CVB200_CANNY_THRESHOLD_TYPE_PERCENT_OF_MEAN     25
+#define CVB200_CANNY_THRESHOLD_TYPE_COMPARE_TO_GRADIENT 26
+#define CVB200_SOBEL_ID                                 27
+#define CVB200_SCHARR_ID                                28
+#define CVB200_PREWITT_ID                               29
+#define CVB200_HOUGHSHT_ID                              30
+#define CVB200_HOUGHKHT_ID                              31
+#define CVB200_HOUGH_SET_FLT32_RHO                      32
+#define CVB200_HOUGH_SET_FLT32_THETA                    33
+#define CVB200_HOUGH_SET_INT_THRESHOLD                  34
+#define CVB200_HOUGH_SET_INT_MAXLINES                   35
+#define CVB200_HOUGHKHT_SET_FLT32_CLUSTER_MIN_DEVIATION 36
+#define CVB200_HOUGHKHT_SET_INT_CLUSTER_MIN_SIZE        37
+#define CVB200_HOUGHKHT_SET_FLT32_KERNEL_MIN_HEIGTH     38
+#define CVB200_HOUGHKHT_SET_BOOL_OVERRIDE_INPUT_EDGES   39
+#define CVB200_HOUGHKHT_GET_FLT64_GS                    40
+#define CVB200_HOGS_ID                                  41
+#define CVB200_HOG_SET_BOOL_GRADIENT_SIGNED             44
+#define CVB200_HOG_SET_INT_BLOCK_NORM                   45
+#define CVB200_HOG_SET_INT_NBINS                        46
+#define CVB200_HOG_SET_INT_INTERPOLATION                47
+#define CVB200_HOG_BLOCK_NORM_NONE                      48
+#define CVB200_HOG_BLOCK_NORM_L1                        49
+#define CVB200_HOG_BLOCK_NORM_L1SQRT                    50
+#define CVB200_HOG_BLOCK_NORM_L2                        51
+#define CVB200_HOG_BLOCK_NORM_L2HYS                     52
+#define CVB200_HOG_INTERPOLATION_NEAREST                53
+#define CVB200_HOG_INTERPOLATION_BILINEAR_LUT           54
+#define CVB200_HOG_INTERPOLATION_BILINEAR               55
+#define CVB200_PLSL_ID                                  1   /* compv_ccl.h enum (separate id space) */
+#define CVB200_LMSER_ID                                 19
+
+/* Extension (not a reference id): Sobel/Scharr/Prewitt objects only, bool. When true, gmax is taken over the columns x with
+ * x%8 in {0,1,2,4} -- what the reference's x86 SSE4.1 leaf CompVMathUtilsMax_16u_Intrin_SSE41 actually computes
+ * (base/math/intrin/x86/compv_math_utils_intrin_sse41.cxx:55-63 folds only lanes 0,1,2,4). Default false = the true maximum,
+ * i.e. the reference's plain C++ path (compv_math_utils.h:158-170). */
+#define CVB200_EDGE_SET_BOOL_X86_SSE41_GMAX_LANES       1000
+
+/* COMPV_BORDER_TYPE (compv_common.h) */
+#define CVB200_BORDER_TYPE_ZERO      0
+#define CVB200_BORDER_TYPE_IGNORE    1
+#define CVB200_BORDER_TYPE_REPLICATE 2
+
+typedef void* cvb200_stream_t; /* cudaStream_t */
+
+/* ================================================================================================
+ * Runtime. Replaces CompVGpu::init's dlopen("libcuda")/cuInit probe (gpu/compv_gpu.cxx:36-62).
+ * ============================================================================================== */
+/* Binds the calling process to CUDA device `device` (>=0). Must be called before anything else. Idempotent. */
+CVB200_API int cvb200_init(int device);
+CVB200_API int cvb200_deinit(void);
+/* 1 when cvb200_init succeeded (reference: CompVGpu::isActiveAndEnabled, gpu/include/compv/gpu/compv_gpu.h:31-33) */
+CVB200_API int cvb200_is_active(void);
+CVB200_API int cvb200_device_count(int* count);
+CVB200_API const char* cvb200_error_string(int code);
+/* Last CUDA runtime error string seen by the library on this thread ("" if none) */
+CVB200_API const char* cvb200_last_cuda_error(void);
+/* Number of kernel launches issued by this library since load (all threads); used by bench.py's gpu_launches */
+CVB200_API uint64_t cvb200_launch_count(void);
+/* Per-kernel device timing: between _begin and _end every kernel launched by the library is bracketed by CUDA events on its stream.
+ * _end synchronises the device and writes one "name count total_ms\n" line per kernel into buf. Used by bench.py's roofline block. */
+CVB200_API int cvb200_profile_begin(void);
+CVB200_API int cvb200_profile_end(char* buf, size_t bufSize);
+/* Memory helpers so that a host without the CUDA runtime headers can own device / pinned buffers */
+CVB200_API int cvb200_malloc(void** dptr, size_t bytes);
+CVB200_API int cvb200_free(void* dptr);
+CVB200_API int cvb200_host_alloc(void** hptr, size_t bytes);   /* pinned */
+CVB200_API int cvb200_host_free(void* hptr);
+CVB200_API int cvb200_memcpy_h2d(void* dptr, const void* hptr, size_t bytes, cvb200_stream_t stream);
+CVB200_API int cvb200_memcpy_d2h(void* hptr, const void* dptr, size_t bytes, cvb200_stream_t stream);
+CVB200_API int cvb200_memset(void* dptr, int value, size_t bytes, cvb200_stream_t stream);
+CVB200_API int cvb200_stream_create(cvb200_stream_t* stream);
+CVB200_API int cvb200_stream_destroy(cvb200_stream_t stream);
+CVB200_API int cvb200_stream_sync(cvb200_stream_t stream);
+
+/* ================================================================================================
+ * a2 -- separable convolution. Replaces CompVMathConvlt::convlt1<In,Kern,Out> / convlt1FixedPoint
+ * (base/include/compv/base/math/compv_math_convlt.h:25-55, leaves :332-405). Correlation (no kernel flip),
+ * horizontal pass first, intermediate stored as OutputType with the reference's saturation/truncation,
+ * then vertical pass. borderType applies to the r=kernSize/2 outer ring: ZERO writes 0 there, REPLICATE copies
+ * the (saturated) input there, IGNORE leaves it untouched.
+ * kernSize must be odd, <= 63, <= width and <= height. out may not alias in.
+ * ============================================================================================== */
+CVB200_API int cvb200_convlt1_8u16s16s(const uint8_t* in, size_t width, size_t height, size_t stride, const int16_t* vtKern, const int16_t* hzKern, size_t kernSize, int16_t* out, int borderType);
+CVB200_API int cvb200_convlt1_16s16s16s(const int16_t* in, size_t width, size_t height, size_t stride, const int16_t* vtKern, const int16_t* hzKern, size_t kernSize, int16_t* out, int borderType);
+CVB200_API int cvb200_convlt1_8u32f8u(const uint8_t* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, uint8_t* out, int borderType);
+CVB200_API int cvb200_convlt1_8u32f32f(const uint8_t* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, float* out, int borderType);
+CVB200_API int cvb200_convlt1_32f32f32f(const float* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, float* out, int borderType);
+CVB200_API int cvb200_convlt1_32f32f8u(const float* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, uint8_t* out, int borderType);
+CVB200_API int cvb200_convlt1_fxp_8u16u8u(const uint8_t* in, size_t width, size_t height, size_t stride, const uint16_t* vtKern, const uint16_t* hzKern, size_t kernSize, uint8_t* out, int borderType);
+/* device-pointer, batched, asynchronous variants (kernels are HOST pointers: they are passed by value to the launch) */
+CVB200_API int cvb200_convlt1_8u16s16s_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const int16_t* vtKern, const int16_t* hzKern, size_t kernSize, int16_t* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_convlt1_16s16s16s_dev(const int16_t* in, size_t width, size_t height, size_t stride, const int16_t* vtKern, const int16_t* hzKern, size_t kernSize, int16_t* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_convlt1_8u32f8u_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, uint8_t* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_convlt1_8u32f32f_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, float* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_convlt1_32f32f32f_dev(const float* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, float* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_convlt1_32f32f8u_dev(const float* in, size_t width, size_t height, size_t stride, const float* vtKern, const float* hzKern, size_t kernSize, uint8_t* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_convlt1_fxp_8u16u8u_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const uint16_t* vtKern, const uint16_t* hzKern, size_t kernSize, uint8_t* out, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* CompVMathGauss::kernelDim1<float> / kernelDim1FixedPoint (base/include/compv/base/math/compv_math_gauss.h:23-56,
+ * base/math/compv_math_gauss.cxx) -- host-side helpers (5 taps of arithmetic, no pixel work). */
+CVB200_API int cvb200_gauss_kernel_dim1_32f(size_t size, float sigma, float* kernel);
+CVB200_API int cvb200_gauss_kernel_dim1_fxp(size_t size, float sigma, uint16_t* kernel);
+
+/* ================================================================================================
+ * a3/a5 -- edge detectors. Replaces CompVEdgeDete::newObj(&d, id, tLow, tHigh, kernSize) + d->process(image,&edges)
+ * (base/compv_features.cxx:146-161; Sobel/Scharr/Prewitt: core/features/edges/compv_core_feature_edge_dete.cxx:55-206;
+ * Canny: core/features/edges/compv_core_feature_canny_dete.cxx:123-331).
+ * id in {CVB200_SOBEL_ID, CVB200_SCHARR_ID, CVB200_PREWITT_ID, CVB200_CANNY_ID}.
+ * ============================================================================================== */
+typedef struct cvb200_edge_dete cvb200_edge_dete_t;
+CVB200_API int cvb200_edge_dete_new(cvb200_edge_dete_t** dete, int id, float tLow, float tHigh, size_t kernSize);
+CVB200_API int cvb200_edge_dete_free(cvb200_edge_dete_t** dete);
+/* CompVCaps::set (canny_dete.cxx:77-117): CANNY_SET_INT_THRESHOLD_TYPE (int32), CANNY_SET_FLT32_THRESHOLD_LOW/HIGH (float), CANNY_SET_INT_KERNEL_SIZE (int) */
+CVB200_API int cvb200_edge_dete_set(cvb200_edge_dete_t* dete, int id, const void* valuePtr, size_t valueSize);
+/* Optional fused Gaussian pre-blur (BASELINE config 2: CompVMathGauss::kernelDim1<float>(size,sigma) + convlt1<u8,f32,u8> before process()).
+ * size 0 disables. Bit-identical to running cvb200_convlt1_8u32f8u first, but the blurred frame never touches HBM. Canny only. */
+CVB200_API int cvb200_edge_dete_set_preblur(cvb200_edge_dete_t* dete, size_t size, float sigma);
+/* edges: height*stride bytes, same stride as image (canny_dete.cxx:249). edges == image is allowed for the host variant (canny_dete.cxx:122). */
+CVB200_API int cvb200_edge_dete_process(cvb200_edge_dete_t* dete, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges);
+/* Many frames in host memory (pinned memory recommended): chunks are pipelined H2D / kernels / D2H on three streams. Synchronous. */
+CVB200_API int cvb200_edge_dete_process_batch(cvb200_edge_dete_t* dete, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges, size_t batch, size_t framePitch);
+CVB200_API int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* dete, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* Intermediate gradient planes of the Canny/Sobel front end (K1+K4: convlt1<u8,int16,int16> x2 + CompVMathUtils::sumAbs,
+ * canny_dete.cxx:236-240): gx, gy int16 and g uint16, each height*stride samples. Any of the three outputs may be NULL. */
+CVB200_API int cvb200_sobel_g(const uint8_t* image, size_t width, size_t height, size_t stride, int id, size_t kernSize, int16_t* gx, int16_t* gy, uint16_t* g);
+CVB200_API int cvb200_sobel_g_dev(const uint8_t* image, size_t width, size_t height, size_t stride, int id, size_t kernSize, int16_t* gx, int16_t* gy, uint16_t* g, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CVB200_H_ */

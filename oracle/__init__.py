@@ -1,0 +1,214 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy/ctypes front end of the two CPU checkers:
+
+  * `orc`  : oracle/libcompv_oracle.so, the plain-C restatement (oracle/compv_oracle*.c), built by `make -C oracle`;
+  * `ref`  : oracle/_ref/libcompv_refshim.so, the UNMODIFIED reference compiled from /root/reference by oracle/build_ref.sh
+             (present here and, as a prebuilt .so, on the GPU box; never rebuilt there).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this package.  The product (compv_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "libcompv_oracle.so")
+REFSHIM_SO = os.path.join(_HERE, "_ref", "libcompv_refshim.so")
+
+_orc = None
+_ref = None
+_ref_threads = None
+
+
+def build(verbose=False):
+    """Compile the C restatement and, when /root/reference is present, the reference itself."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", _HERE], stdout=out)
+    if os.path.isdir("/root/reference/base"):
+        subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")], stdout=out)
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        _orc = C.CDLL(ORACLE_SO)
+    return _orc
+
+
+def have_ref():
+    return os.path.exists(REFSHIM_SO)
+
+
+def ref(threads=1):
+    """The compiled reference.  `threads`: 1 = single threaded (CompVBase::init(1)), -1 = one per core."""
+    global _ref, _ref_threads
+    if _ref is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libcompv_refshim.so is missing: run oracle/build_ref.sh where /root/reference exists")
+        _ref = C.CDLL(REFSHIM_SO)
+        _ref.ref_cpu_flags.restype = C.c_char_p
+        rc = _ref.ref_init(int(threads))
+        if rc:
+            raise RuntimeError("ref_init failed: %d" % rc)
+        _ref_threads = threads
+    elif threads != _ref_threads:
+        rc = _ref.ref_set_max_threads(int(threads))
+        if rc:
+            raise RuntimeError("ref_set_max_threads failed: %d" % rc)
+        _ref_threads = threads
+    return _ref
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _sz(v):
+    return C.c_size_t(int(v))
+
+
+def _chk(rc, what):
+    if rc:
+        raise RuntimeError("%s failed: %d" % (what, rc))
+
+
+# numpy dtypes of the convolution variants: name -> (in, kernel, out)
+CONV_TYPES = {
+    "8u16s16s": (np.uint8, np.int16, np.int16),
+    "16s16s16s": (np.int16, np.int16, np.int16),
+    "8u32f8u": (np.uint8, np.float32, np.uint8),
+    "8u32f32f": (np.uint8, np.float32, np.float32),
+    "32f32f32f": (np.float32, np.float32, np.float32),
+    "32f32f8u": (np.float32, np.float32, np.uint8),
+    "fxp_8u16u8u": (np.uint8, np.uint16, np.uint8),
+}
+
+
+def _frame_args(img, width=None):
+    """img is a 2-D array whose row pitch is the stride; `width` (<= pitch) is the logical width."""
+    assert img.ndim == 2 and img.flags.c_contiguous
+    h, stride = img.shape
+    w = stride if width is None else width
+    return w, h, stride
+
+
+def convlt1(which, name, img, vt, hz, width=None, border=0, out=None):
+    """which: 'orc' or 'ref'.  Returns the (h, stride) output plane."""
+    tin, tk, tout = CONV_TYPES[name]
+    assert img.dtype == tin
+    vt = np.ascontiguousarray(vt, dtype=tk)
+    hz = np.ascontiguousarray(hz, dtype=tk)
+    w, h, stride = _frame_args(img, width)
+    if out is None:
+        out = np.zeros((h, stride), dtype=tout)
+    if which == "orc":
+        fn = getattr(orc(), "orc_convlt1_" + name)
+        _chk(fn(_p(img), _sz(w), _sz(h), _sz(stride), _p(vt), _p(hz), _sz(len(vt)), _p(out), int(border)), "orc_convlt1_" + name)
+    else:
+        assert border == 0
+        fn = getattr(ref(), "ref_convlt1_" + name)
+        _chk(fn(_p(img), _sz(w), _sz(h), _sz(stride), _p(vt), _p(hz), _sz(len(vt)), _p(out)), "ref_convlt1_" + name)
+    return out
+
+
+def gauss_kernel(which, size, sigma, fixed_point=False):
+    k = np.zeros(size, dtype=np.uint16 if fixed_point else np.float32)
+    lib, pre = (orc(), "orc") if which == "orc" else (ref(), "ref")
+    fn = getattr(lib, pre + ("_gauss_kernel_dim1_fxp" if fixed_point else "_gauss_kernel_dim1_32f"))
+    _chk(fn(_sz(size), C.c_float(sigma), _p(k)), "gauss_kernel")
+    return k
+
+
+EDGE_WHICH = {"sobel": 0, "scharr": 1, "prewitt": 2, "canny": 3}
+
+
+def sobel_g(which, img, kind="sobel", ks=3, width=None):
+    w, h, stride = _frame_args(img, width)
+    gx = np.zeros((h, stride), np.int16)
+    gy = np.zeros((h, stride), np.int16)
+    g = np.zeros((h, stride), np.uint16)
+    if which == "orc":
+        _chk(orc().orc_sobel_g(_p(img), _sz(w), _sz(h), _sz(stride), EDGE_WHICH[kind], int(ks), _p(gx), _p(gy), _p(g)), "orc_sobel_g")
+    else:
+        tabs = {("sobel", 3): ([1, 2, 1], [-1, 0, 1]), ("sobel", 5): ([1, 4, 6, 4, 1], [1, 2, 0, -2, -1]),
+                ("canny", 3): ([1, 2, 1], [-1, 0, 1]), ("canny", 5): ([1, 4, 6, 4, 1], [1, 2, 0, -2, -1]),
+                ("scharr", 3): ([3, 10, 3], [-1, 0, 1]), ("prewitt", 3): ([1, 1, 1], [-1, 0, 1])}
+        vt, hz = tabs[(kind, ks)]
+        gx = convlt1("ref", "8u16s16s", img, vt, hz, width=width)
+        gy = convlt1("ref", "8u16s16s", img, hz, vt, width=width)
+        _chk(ref().ref_sum_abs_16s16u(_p(gx), _p(gy), _p(g), _sz(w), _sz(h), _sz(stride)), "ref_sum_abs")
+    return gx, gy, g
+
+
+def edge_dete(which, img, kind="canny", tlow=59.0, thigh=119.0, ks=3, width=None, threshold_type=0, threads=1, simd=True, sse41_gmax_lanes=False):
+    """Sobel/Scharr/Prewitt normalised gradient or Canny edge map, (h, stride) uint8.
+    simd=False runs the reference's plain C++ path (CompVCpu::flagsDisable(kCpuFlagAll)); sse41_gmax_lanes: see orc_edge_normalized."""
+    w, h, stride = _frame_args(img, width)
+    out = np.zeros((h, stride), np.uint8)
+    if which == "orc":
+        if kind == "canny":
+            _chk(orc().orc_canny(_p(img), _sz(w), _sz(h), _sz(stride), C.c_float(tlow), C.c_float(thigh), int(ks), int(threshold_type), _p(out)), "orc_canny")
+        else:
+            _chk(orc().orc_edge_normalized(_p(img), _sz(w), _sz(h), _sz(stride), EDGE_WHICH[kind], int(bool(sse41_gmax_lanes)), _p(out)), "orc_edge_normalized")
+    else:
+        r = ref(threads)
+        if not simd:
+            _chk(r.ref_cpu_simd(0), "ref_cpu_simd")
+        try:
+            _chk(r.ref_edge_dete(EDGE_WHICH[kind], _p(img), _sz(w), _sz(h), _sz(stride), C.c_float(tlow), C.c_float(thigh), int(ks),
+                                 int(threshold_type), _p(out)), "ref_edge_dete")
+        finally:
+            if not simd:
+                _chk(r.ref_cpu_simd(1), "ref_cpu_simd")
+    return out
+
+
+def time_edge_dete(img, kind="canny", tlow=59.0, thigh=119.0, ks=3, blur_size=0, blur_sigma=1.0, iters=10, threads=-1, width=None):
+    """Times the reference (ms per iteration, numpy array) -- CompVEdgeDete::process with an optional Gaussian pre-blur."""
+    w, h, stride = _frame_args(img, width)
+    ms = np.zeros(iters, np.float64)
+    out = np.zeros((h, stride), np.uint8)
+    _chk(ref(threads).ref_time_edge_dete(EDGE_WHICH[kind], _p(img), _sz(w), _sz(h), _sz(stride), C.c_float(tlow), C.c_float(thigh), int(ks),
+                                         int(blur_size), C.c_float(blur_sigma), int(iters), _p(ms), _p(out)), "ref_time_edge_dete")
+    return ms, out
+
+
+class RefEdgeSession:
+    """Reference detector + pre-wrapped frames created once; run() times blur (optional) + CompVEdgeDete::process over frames."""
+
+    def __init__(self, frames, kind="canny", tlow=59.0, thigh=119.0, ks=3, blur_size=0, blur_sigma=1.0, threads=-1, width=None):
+        assert frames.ndim == 3 and frames.flags.c_contiguous and frames.dtype == np.uint8
+        n, h, stride = frames.shape
+        w = stride if width is None else width
+        self._r = ref(threads)
+        self._r.ref_edge_session_new.restype = C.c_void_p
+        self._r.ref_edge_session_run.restype = C.c_double
+        self.shape = (h, stride)
+        self.count = n
+        self._s = C.c_void_p(self._r.ref_edge_session_new(EDGE_WHICH[kind], _p(frames), _sz(n), _sz(w), _sz(h), _sz(stride), C.c_float(tlow), C.c_float(thigh),
+                                                          int(ks), int(blur_size), C.c_float(blur_sigma)))
+        if not self._s:
+            raise RuntimeError("ref_edge_session_new failed")
+
+    def run(self, first=0, count=None, want_edges=False):
+        """Returns (elapsed ms, last edge map or None)."""
+        count = self.count if count is None else count
+        out = np.zeros(self.shape, np.uint8) if want_edges else None
+        ms = self._r.ref_edge_session_run(self._s, _sz(first), _sz(count), _p(out), _sz(self.shape[1]))
+        if ms < 0:
+            raise RuntimeError("ref_edge_session_run failed: %r" % ms)
+        return ms, out
+
+    def close(self):
+        if self._s:
+            self._r.ref_edge_session_free(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

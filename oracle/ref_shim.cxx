@@ -1,0 +1,267 @@
+// TEST INFRASTRUCTURE ONLY -- never linked or loaded by the product path (compv_b200/).
+//
+// extern "C" shim over the UNMODIFIED CompV reference library (oracle/_ref/libcompv_ref.so, built by
+// oracle/build_ref.sh from the sources where they lie under /root/reference). It lets the Python tests and
+// bench.py's CPU legs call the reference's own public C++ API through ctypes. It contains no algorithm of its
+// own: every function below is a thin call into the reference API named in its comment.
+#include "compv/base/compv_base.h"
+#include "compv/base/compv_cpu.h"
+#include "compv/base/compv_features.h"
+#include "compv/base/compv_ccl.h"
+#include "compv/base/image/compv_image.h"
+#include "compv/base/math/compv_math_convlt.h"
+#include "compv/base/math/compv_math_gauss.h"
+#include "compv/base/math/compv_math_utils.h"
+#include "compv/base/compv_gradient_fast.h"
+#include "compv/base/parallel/compv_parallel.h"
+#include "compv/core/compv_core.h"
+
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace compv;
+
+#define SHIM_CHECK(x) do { COMPV_ERROR_CODE e__ = (x); if (COMPV_ERROR_CODE_IS_NOK(e__)) return static_cast<int>(e__); } while (0)
+
+static double now_ms()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int wrap8u(const uint8_t* img, size_t w, size_t h, size_t stride, CompVMatPtr* out)
+{
+	// CompVImage::wrap copies into a CompVMat with the requested stride (base/image/compv_image.cxx:381-404)
+	SHIM_CHECK(CompVImage::wrap(COMPV_SUBTYPE_PIXELS_Y, img, w, h, stride, &(*out), stride));
+	return 0;
+}
+
+static void copy_rows(const CompVMatPtr& m, void* dst, size_t dstStrideBytes)
+{
+	const size_t rowBytes = m->rowInBytes();
+	for (size_t j = 0; j < m->rows(); ++j) {
+		memcpy(static_cast<uint8_t*>(dst) + j * dstStrideBytes, m->ptr<const uint8_t>(j), rowBytes);
+	}
+}
+
+extern "C" {
+
+// CompVBase::init + CompVCore::init (base/compv_base.cxx, core/compv_core.cxx:149-164). numThreads=-1 -> one per core.
+int ref_init(int numThreads)
+{
+	CompVDebugMgr::setLevel(COMPV_DEBUG_LEVEL_ERROR);
+	SHIM_CHECK(CompVBase::init(numThreads));
+	SHIM_CHECK(CompVCore::init());
+	return 0;
+}
+
+int ref_deinit()
+{
+	SHIM_CHECK(CompVCore::deInit());
+	SHIM_CHECK(CompVBase::deInit());
+	return 0;
+}
+
+int ref_set_max_threads(int n)
+{
+	SHIM_CHECK(CompVParallel::multiThreadingSetMaxThreads(n));
+	return 0;
+}
+
+int ref_threads_count()
+{
+	CompVThreadDispatcherPtr d = CompVParallel::threadDispatcher();
+	return d ? static_cast<int>(d->threadsCount()) : 1;
+}
+
+// CompVCpu::flagsDisable / flagsEnable: select the plain C++ path (all flags off) or the SIMD path
+int ref_cpu_simd(int enable)
+{
+	if (enable) {
+		SHIM_CHECK(CompVCpu::flagsEnable(kCpuFlagAll));
+		SHIM_CHECK(CompVCpu::setIntrinsicsEnabled(true));
+	}
+	else {
+		SHIM_CHECK(CompVCpu::flagsDisable(kCpuFlagAll));
+		SHIM_CHECK(CompVCpu::setIntrinsicsEnabled(false));
+	}
+	return 0;
+}
+
+const char* ref_cpu_flags()
+{
+	static std::string s;
+	s = CompVCpu::flagsAsString(CompVCpu::getFlags());
+	return s.c_str();
+}
+
+// ---- K1..K3: CompVMathConvlt::convlt1<...> (base/include/compv/base/math/compv_math_convlt.h:25-55) ----
+int ref_convlt1_8u16s16s(const uint8_t* in, size_t w, size_t h, size_t stride, const int16_t* vt, const int16_t* hz, size_t k, int16_t* out)
+{
+	SHIM_CHECK((CompVMathConvlt::convlt1<uint8_t, int16_t, int16_t>(in, w, h, stride, vt, hz, k, out)));
+	return 0;
+}
+int ref_convlt1_16s16s16s(const int16_t* in, size_t w, size_t h, size_t stride, const int16_t* vt, const int16_t* hz, size_t k, int16_t* out)
+{
+	SHIM_CHECK((CompVMathConvlt::convlt1<int16_t, int16_t, int16_t>(in, w, h, stride, vt, hz, k, out)));
+	return 0;
+}
+int ref_convlt1_8u32f8u(const uint8_t* in, size_t w, size_t h, size_t stride, const float* vt, const float* hz, size_t k, uint8_t* out)
+{
+	SHIM_CHECK((CompVMathConvlt::convlt1<uint8_t, compv_float32_t, uint8_t>(in, w, h, stride, vt, hz, k, out)));
+	return 0;
+}
+int ref_convlt1_8u32f32f(const uint8_t* in, size_t w, size_t h, size_t stride, const float* vt, const float* hz, size_t k, float* out)
+{
+	SHIM_CHECK((CompVMathConvlt::convlt1<uint8_t, compv_float32_t, compv_float32_t>(in, w, h, stride, vt, hz, k, out)));
+	return 0;
+}
+int ref_convlt1_32f32f32f(const float* in, size_t w, size_t h, size_t stride, const float* vt, const float* hz, size_t k, float* out)
+{
+	SHIM_CHECK((CompVMathConvlt::convlt1<compv_float32_t, compv_float32_t, compv_float32_t>(in, w, h, stride, vt, hz, k, out)));
+	return 0;
+}
+int ref_convlt1_32f32f8u(const float* in, size_t w, size_t h, size_t stride, const float* vt, const float* hz, size_t k, uint8_t* out)
+{
+	SHIM_CHECK((CompVMathConvlt::convlt1<compv_float32_t, compv_float32_t, uint8_t>(in, w, h, stride, vt, hz, k, out)));
+	return 0;
+}
+int ref_convlt1_fxp_8u16u8u(const uint8_t* in, size_t w, size_t h, size_t stride, const uint16_t* vt, const uint16_t* hz, size_t k, uint8_t* out)
+{
+	SHIM_CHECK(CompVMathConvlt::convlt1FixedPoint(in, w, h, stride, vt, hz, k, out));
+	return 0;
+}
+
+// CompVMathGauss::kernelDim1<float> (base/include/compv/base/math/compv_math_gauss.h:23-56)
+int ref_gauss_kernel_dim1_32f(size_t size, float sigma, float* out)
+{
+	CompVMatPtr kernel;
+	SHIM_CHECK(CompVMathGauss::kernelDim1<compv_float32_t>(&kernel, size, sigma));
+	memcpy(out, kernel->ptr<const compv_float32_t>(), size * sizeof(float));
+	return 0;
+}
+// CompVMathGauss::kernelDim1FixedPoint (base/math/compv_math_gauss.cxx)
+int ref_gauss_kernel_dim1_fxp(size_t size, float sigma, uint16_t* out)
+{
+	CompVMatPtr kernel;
+	SHIM_CHECK(CompVMathGauss::kernelDim1FixedPoint(&kernel, size, sigma));
+	memcpy(out, kernel->ptr<const uint16_t>(), size * sizeof(uint16_t));
+	return 0;
+}
+
+// K4: CompVMathUtils::sumAbs<int16_t,uint16_t> (base/math/compv_math_utils.cxx:211-246)
+int ref_sum_abs_16s16u(const int16_t* a, const int16_t* b, uint16_t* r, size_t w, size_t h, size_t stride)
+{
+	SHIM_CHECK((CompVMathUtils::sumAbs<int16_t, uint16_t>(a, b, r, w, h, stride)));
+	return 0;
+}
+
+// ---- a3/a5: CompVEdgeDete (Sobel/Scharr/Prewitt/Canny) through the factory (base/compv_features.cxx:146-161) ----
+// which: 0=Sobel 1=Scharr 2=Prewitt 3=Canny
+// thresholdType: 0 = COMPV_CANNY_THRESHOLD_TYPE_COMPARE_TO_GRADIENT (default), 1 = ..._PERCENT_OF_MEAN (Canny only)
+int ref_edge_dete(int which, const uint8_t* img, size_t w, size_t h, size_t stride, float tLow, float tHigh, int kernSize, int thresholdType, uint8_t* edges /* h*stride */)
+{
+	static const int ids[4] = { COMPV_SOBEL_ID, COMPV_SCHARR_ID, COMPV_PREWITT_ID, COMPV_CANNY_ID };
+	CompVMatPtr image, out;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVEdgeDetePtr dete;
+	SHIM_CHECK(CompVEdgeDete::newObj(&dete, ids[which & 3], tLow, tHigh, static_cast<size_t>(kernSize)));
+	if ((which & 3) == 3 && thresholdType == 1) {
+		SHIM_CHECK(dete->setInt(COMPV_CANNY_SET_INT_THRESHOLD_TYPE, COMPV_CANNY_THRESHOLD_TYPE_PERCENT_OF_MEAN));
+	}
+	SHIM_CHECK(dete->process(image, &out));
+	copy_rows(out, edges, stride);
+	return 0;
+}
+
+// Timed variant of the above: object created once, 1 warm-up, `iters` timed iterations (steady_clock), per-iteration ms written to msOut[iters].
+// Optional Gaussian pre-blur (blurSize>0): CompVMathGauss::kernelDim1<float> + CompVMathConvlt::convlt1<u8,f32,u8> in the timed loop (BASELINE config 2).
+int ref_time_edge_dete(int which, const uint8_t* img, size_t w, size_t h, size_t stride, float tLow, float tHigh, int kernSize,
+	int blurSize, float blurSigma, int iters, double* msOut, uint8_t* edges)
+{
+	static const int ids[4] = { COMPV_SOBEL_ID, COMPV_SCHARR_ID, COMPV_PREWITT_ID, COMPV_CANNY_ID };
+	CompVMatPtr image, blurred, out, kernel;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVEdgeDetePtr dete;
+	SHIM_CHECK(CompVEdgeDete::newObj(&dete, ids[which & 3], tLow, tHigh, static_cast<size_t>(kernSize)));
+	if (blurSize > 0) {
+		SHIM_CHECK(CompVMathGauss::kernelDim1<compv_float32_t>(&kernel, static_cast<size_t>(blurSize), blurSigma));
+		SHIM_CHECK(CompVImage::newObj8u(&blurred, COMPV_SUBTYPE_PIXELS_Y, w, h, stride));
+	}
+	for (int it = -1; it < iters; ++it) {
+		const double t0 = now_ms();
+		if (blurSize > 0) {
+			uint8_t* bptr = blurred->ptr<uint8_t>();
+			SHIM_CHECK((CompVMathConvlt::convlt1<uint8_t, compv_float32_t, uint8_t>(image->ptr<const uint8_t>(), w, h, stride,
+				kernel->ptr<const compv_float32_t>(), kernel->ptr<const compv_float32_t>(), static_cast<size_t>(blurSize), bptr)));
+			SHIM_CHECK(dete->process(blurred, &out));
+		}
+		else {
+			SHIM_CHECK(dete->process(image, &out));
+		}
+		const double t1 = now_ms();
+		if (it >= 0) msOut[it] = t1 - t0;
+	}
+	if (edges) copy_rows(out, edges, stride);
+	return 0;
+}
+
+// Persistent edge-detection session for bench.py's CPU legs: frames are wrapped once (CompVImage::wrap), the detector, the Gaussian kernel and the
+// output matrices are created once, then ref_edge_session_run() times CompVMathConvlt::convlt1<u8,f32,u8> (optional) + CompVEdgeDete::process per frame.
+struct RefEdgeSession {
+	std::vector<CompVMatPtr> frames;
+	CompVMatPtr blurred, out, kernel;
+	CompVEdgeDetePtr dete;
+	int blurSize;
+};
+
+void* ref_edge_session_new(int which, const uint8_t* frames, size_t count, size_t w, size_t h, size_t stride, float tLow, float tHigh, int kernSize, int blurSize, float blurSigma)
+{
+	static const int ids[4] = { COMPV_SOBEL_ID, COMPV_SCHARR_ID, COMPV_PREWITT_ID, COMPV_CANNY_ID };
+	RefEdgeSession* s = new RefEdgeSession();
+	s->blurSize = blurSize;
+	for (size_t i = 0; i < count; ++i) {
+		CompVMatPtr m;
+		if (wrap8u(frames + i * stride * h, w, h, stride, &m)) { delete s; return NULL; }
+		s->frames.push_back(m);
+	}
+	if (COMPV_ERROR_CODE_IS_NOK(CompVEdgeDete::newObj(&s->dete, ids[which & 3], tLow, tHigh, static_cast<size_t>(kernSize)))) { delete s; return NULL; }
+	if (blurSize > 0) {
+		if (COMPV_ERROR_CODE_IS_NOK(CompVMathGauss::kernelDim1<compv_float32_t>(&s->kernel, static_cast<size_t>(blurSize), blurSigma))
+			|| COMPV_ERROR_CODE_IS_NOK(CompVImage::newObj8u(&s->blurred, COMPV_SUBTYPE_PIXELS_Y, w, h, stride))) { delete s; return NULL; }
+	}
+	return s;
+}
+
+// Processes frames[first .. first+count) (indices wrap around); returns elapsed milliseconds (steady_clock) or a negative error code.
+double ref_edge_session_run(void* session, size_t first, size_t count, uint8_t* lastEdges, size_t stride)
+{
+	RefEdgeSession* s = static_cast<RefEdgeSession*>(session);
+	if (!s || s->frames.empty()) return -1.0;
+	const double t0 = now_ms();
+	for (size_t i = 0; i < count; ++i) {
+		const CompVMatPtr& image = s->frames[(first + i) % s->frames.size()];
+		if (s->blurSize > 0) {
+			uint8_t* bptr = s->blurred->ptr<uint8_t>();
+			if (COMPV_ERROR_CODE_IS_NOK((CompVMathConvlt::convlt1<uint8_t, compv_float32_t, uint8_t>(image->ptr<const uint8_t>(), image->cols(), image->rows(), image->stride(),
+				s->kernel->ptr<const compv_float32_t>(), s->kernel->ptr<const compv_float32_t>(), static_cast<size_t>(s->blurSize), bptr)))) return -2.0;
+			if (COMPV_ERROR_CODE_IS_NOK(s->dete->process(s->blurred, &s->out))) return -3.0;
+		}
+		else {
+			if (COMPV_ERROR_CODE_IS_NOK(s->dete->process(image, &s->out))) return -3.0;
+		}
+	}
+	const double t1 = now_ms();
+	if (lastEdges && s->out) copy_rows(s->out, lastEdges, stride);
+	return t1 - t0;
+}
+
+void ref_edge_session_free(void* session)
+{
+	delete static_cast<RefEdgeSession*>(session);
+}
+
+} // extern "C"

@@ -1,0 +1,57 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/cvb200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "cvb200.h")).read()
+    return sorted(set(re.findall(r"CVB200_API\s+[\w\s\*]+?\b(cvb200_\w+)\s*\(", txt)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for must in ["cvb200_init", "cvb200_convlt1_8u16s16s", "cvb200_edge_dete_process", "cvb200_edge_dete_process_dev", "cvb200_sobel_g"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from compv_b200 import _ffi
+    assert os.path.exists(_ffi.LIB_PATH), "libcompv_b200.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, "declared in include/cvb200.h but not exported: %s" % missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the library must refuse (E_CUDA / E_NOT_INITIALIZED), never compute on the CPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from compv_b200 import _ffi
+    lib = _ffi.lib()
+    assert lib.cvb200_init(0) == _ffi.E_CUDA
+    assert lib.cvb200_is_active() == 0
+    img = np.zeros((16, 16), np.uint8)
+    out = np.zeros((16, 16), np.int16)
+    k = np.array([1, 2, 1], np.int16)
+    rc = lib.cvb200_convlt1_8u16s16s(_ffi.vp(img), _ffi.sz(16), _ffi.sz(16), _ffi.sz(16), _ffi.vp(k), _ffi.vp(k), _ffi.sz(3), _ffi.vp(out), 0)
+    assert rc == _ffi.E_NOT_INITIALIZED
+    h = ctypes.c_void_p()
+    assert lib.cvb200_edge_dete_new(ctypes.byref(h), _ffi.CANNY_ID, ctypes.c_float(59), ctypes.c_float(119), _ffi.sz(3)) == _ffi.E_NOT_INITIALIZED
+
+
+def test_product_never_references_the_oracle():
+    """The product path must not reference oracle/ (parity claims are void otherwise)."""
+    pkg = os.path.join(ROOT, "compv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".cxx", ".h", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("import oracle", "from oracle", "libcompv_oracle", "libcompv_ref"):
+                    assert needle not in txt, "%s mentions %s" % (os.path.join(dirpath, f), needle)

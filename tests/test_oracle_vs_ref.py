@@ -1,0 +1,112 @@
+"""Pins the C restatement (oracle/compv_oracle.c) against the UNMODIFIED reference (oracle/_ref) -- CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from frames import frame_g, frame_uniform, frame_smooth, frame_const
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+SIZES = [(64, 48, 64), (100, 37, 128), (257, 65, 320), (640, 480, 640)]
+
+
+def _frames(w, h, stride):
+    return [frame_g(w, h, 12345, stride), frame_uniform(w, h, 1, stride), frame_smooth(w, h, 3, stride)]
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,stride", SIZES)
+@pytest.mark.parametrize("name,ks", [("8u16s16s", 3), ("8u16s16s", 5), ("8u32f8u", 5), ("8u32f8u", 7), ("8u32f32f", 5), ("fxp_8u16u8u", 5), ("fxp_8u16u8u", 3)])
+def test_convlt_from_u8(name, ks, w, h, stride):
+    tin, tk, tout = oracle.CONV_TYPES[name]
+    img = frame_g(w, h, 99, stride)
+    if tk == np.int16:
+        vt = np.array([1, 4, 6, 4, 1][:ks] if ks == 5 else [1, 2, 1], np.int16)
+        hz = np.array([1, 2, 0, -2, -1] if ks == 5 else [-1, 0, 1], np.int16)
+    elif tk == np.float32:
+        vt = hz = oracle.gauss_kernel("ref", ks, 1.3)
+    else:
+        vt = hz = oracle.gauss_kernel("ref", ks, 1.3, fixed_point=True)
+    a = oracle.convlt1("orc", name, img, vt, hz, width=w)
+    b = oracle.convlt1("ref", name, img, vt, hz, width=w)
+    if tout == np.float32:
+        np.testing.assert_array_equal(a[:, :w].view(np.uint32), b[:, :w].view(np.uint32))
+    else:
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["16s16s16s", "32f32f32f", "32f32f8u"])
+def test_convlt_other_inputs(name):
+    tin, tk, tout = oracle.CONV_TYPES[name]
+    w, h, stride = 200, 90, 256
+    rng = np.random.default_rng(5)
+    if tin == np.int16:
+        img = rng.integers(-3000, 3000, (h, stride)).astype(np.int16)
+        vt = np.array([3, -7, 11, -7, 3], np.int16)  # large enough to hit the int16 saturation
+        hz = np.array([9, 14, -5, 14, 9], np.int16)
+    else:
+        img = (rng.random((h, stride)) * 300 - 20).astype(np.float32)
+        vt = hz = oracle.gauss_kernel("ref", 7, 2.0)
+    a = oracle.convlt1("orc", name, img, vt, hz, width=w)
+    b = oracle.convlt1("ref", name, img, vt, hz, width=w)
+    if tout == np.float32:
+        np.testing.assert_array_equal(a[:, :w].view(np.uint32), b[:, :w].view(np.uint32))
+    else:
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
+
+
+@needs_ref
+def test_gauss_kernels():
+    for size, sigma in [(3, 0.8), (5, 1.0), (7, 2.0), (9, 1.7)]:
+        np.testing.assert_array_equal(oracle.gauss_kernel("orc", size, sigma).view(np.uint32), oracle.gauss_kernel("ref", size, sigma).view(np.uint32))
+        np.testing.assert_array_equal(oracle.gauss_kernel("orc", size, sigma, True), oracle.gauss_kernel("ref", size, sigma, True))
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,stride", SIZES)
+@pytest.mark.parametrize("kind,ks", [("sobel", 3), ("sobel", 5), ("scharr", 3), ("prewitt", 3)])
+def test_sobel_g(kind, ks, w, h, stride):
+    for img in _frames(w, h, stride):
+        a = oracle.sobel_g("orc", img, kind, ks, width=w)
+        b = oracle.sobel_g("ref", img, kind, ks, width=w)
+        for pa, pb in zip(a, b):
+            np.testing.assert_array_equal(pa[:, :w], pb[:, :w])
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,stride", SIZES)
+@pytest.mark.parametrize("kind", ["sobel", "scharr", "prewitt"])
+def test_edge_normalized(kind, w, h, stride):
+    for img in _frames(w, h, stride) + [frame_const(w, h, 77, stride)]:
+        # the reference's plain C++ path takes the true gmax ...
+        a = oracle.edge_dete("orc", img, kind, width=w)
+        b = oracle.edge_dete("ref", img, kind, width=w, simd=False)
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
+        # ... its x86 SSE4.1 leaf only folds lanes 0,1,2,4 of the running maximum (see orc_edge_normalized)
+        a = oracle.edge_dete("orc", img, kind, width=w, sse41_gmax_lanes=True)
+        b = oracle.edge_dete("ref", img, kind, width=w, simd=True)
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,stride", SIZES + [(1920, 1080, 1920)])
+@pytest.mark.parametrize("ks,tlow,thigh", [(3, 59.0, 119.0), (3, 20.0, 300.0), (5, 300.0, 900.0)])
+def test_canny(ks, tlow, thigh, w, h, stride):
+    for img in _frames(w, h, stride) + [frame_const(w, h, 0, stride)]:
+        a = oracle.edge_dete("orc", img, "canny", tlow, thigh, ks, width=w)
+        # When (W-1) % 16 == 0 the reference's AVX2 NMS / SSE2 hysteresis leaves skip the last 15 columns and no scalar tail runs
+        # (canny_dete.cxx:396,514: colStart = (W-1) & -15 == W-1), so its SIMD path disagrees with its own C++ path; the C++ path is the spec.
+        simd = ((w - 1) % 16) != 0
+        for threads in (1, -1):  # the reference's own invariant: thread count does not change the bytes
+            b = oracle.edge_dete("ref", img, "canny", tlow, thigh, ks, width=w, threads=threads, simd=simd)
+            np.testing.assert_array_equal(a[:, :w], b[:, :w])
+
+
+@needs_ref
+def test_canny_percent_of_mean():
+    w, h, stride = 320, 200, 320
+    for img in _frames(w, h, stride):
+        a = oracle.edge_dete("orc", img, "canny", 0.8, 1.6, 3, width=w, threshold_type=1)
+        b = oracle.edge_dete("ref", img, "canny", 0.8, 1.6, 3, width=w, threshold_type=1)
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
