@@ -85,6 +85,7 @@ class CompVEdgeDete:
     """Mirror of CompVEdgeDete (base/include/compv/base/compv_features.h:205-215) over cvb200_edge_dete_*."""
 
     EDGE_SET_BOOL_X86_SSE41_GMAX_LANES = 1000
+    EDGE_SET_BOOL_GENERIC_KERNEL = 1001
 
     def __init__(self, handle, dete_id):
         self._h = handle

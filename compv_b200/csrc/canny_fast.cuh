@@ -1,0 +1,366 @@
+// Fast path of the Canny front end for the common configuration: Sobel 3x3 with an optional fused 3- or 5-tap Gaussian.
+// Same arithmetic contract as edge_front_kernel<3,0> in edges.cu (that generic kernel stays as the fallback for Sobel 5x5,
+// 7-tap blurs and strides TMA cannot address), restructured for issue rate:
+//   * the (120+8) x (60+2*(rb+2)) u8 input tile lands in shared memory through ONE TMA bulk-tensor copy per CTA
+//     (cp.async.bulk.tensor.3d, out-of-image elements zero-filled by the hardware) -- no per-pixel load instructions;
+//   * every lane owns 4 consecutive pixels (one 32-bit shared-memory word per row): all shared-memory traffic is 32/64-bit and conflict free;
+//   * u8 <-> f32 conversions use the 2^23 magic-number trick (PRMT + FADD / FADD.RZ) instead of the quarter-rate I2F/F2I pipe;
+//   * gx/gy never reach shared memory: the gradient stage stores g (11 bits for Sobel 3x3) with the 2-bit NMS direction in bits 14-15.
+// Tile geometry: a warp's 32 lanes x 4 px = 128 columns [x0-4, x0+124); blurred columns valid on [x0-2, x0+122), g on [x0-1, x0+121),
+// output on [x0, x0+120) (lanes 1..30).  120 divides 1920 and 3840, 60 divides 1080, 2160 and 480.
+#pragma once
+
+#include <cuda.h>
+
+namespace cvb {
+
+constexpr int CF_TW = 120, CF_TH = 60, CF_THREADS = 256, CF_WARPS = 8;
+constexpr int CF_ROWW = 32;           // words per row of the intermediate tiles (128 bytes)
+constexpr int CF_INW = 36;            // words per row of the TMA-staged input tile: the box is 144 bytes wide because the innermost TMA
+                                      // coordinate must be a multiple of 16 bytes: origin = (x0-4) & ~15, my word = woff + lane, woff in {1, 3}
+constexpr int CF_PAD = 4;             // pad words before each array: lane-1 / lane+1 over-reads stay inside the allocation
+
+template <int BKS>
+struct CFGeom {
+	static constexpr int RB = BKS >> 1;
+	static constexpr int IN_ROWS = CF_TH + 2 * (RB + 2);   // image rows y0-RB-2 .. y0+TH+RB+1
+	static constexpr int B_ROWS = CF_TH + 4;                // y0-2 .. y0+TH+1
+	static constexpr int G_ROWS = CF_TH + 2;                // y0-1 .. y0+TH
+	// word offsets inside dynamic shared memory
+	static constexpr int OFF_A = CF_PAD;                                  // input tile, later the blurred tile
+	static constexpr int OFF_M = OFF_A + IN_ROWS * CF_INW + CF_PAD;       // horizontally blurred tile
+	static constexpr int OFF_G = OFF_M + (BKS ? IN_ROWS * CF_ROWW : 0) + CF_PAD; // g|dir (u16 x 128 per row = 64 words)
+	static constexpr int WORDS = OFF_G + G_ROWS * 64 + CF_PAD;
+	static constexpr size_t SMEM = WORDS * 4 + 512; // + 128-byte alignment slack, the 32 pad words in front of sA and the mbarrier
+};
+
+struct FastParams {
+	const uint8_t* in;      // used only by the non-TMA loader
+	uint8_t* cls;
+	const ushort2* thr;
+	int W, H;
+	size_t stride, framePitch;
+	int tLow, tHigh;
+	float k[5];
+	int useTma;
+	int vecStore;           // cls rows are 4-byte aligned
+};
+
+__device__ __forceinline__ float u8_to_f32(unsigned int w, int byteIdx)
+{
+	// [b, 0, 0, 0x4B] = 2^23 + b as a float; subtracting 2^23 is exact
+	return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | byteIdx)) - 8388608.f;
+}
+
+// trunc(clamp(s, 0, 255)) in the low byte of the returned bit pattern (2^23 magic add, round toward zero)
+__device__ __forceinline__ unsigned int f32_to_u8_bits(float s)
+{
+	s = fminf(fmaxf(s, 0.f), 255.f);
+	return __float_as_uint(__fadd_rz(s, 8388608.f));
+}
+
+__device__ __forceinline__ unsigned int pack4(unsigned int a, unsigned int b, unsigned int c, unsigned int d)
+{
+	return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase)
+{
+	const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+	unsigned ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(phase) : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* smemDst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+		:: "r"(static_cast<unsigned>(__cvta_generic_to_shared(smemDst))), "l"(reinterpret_cast<uint64_t>(map)),
+		   "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(c0), "r"(c1), "r"(c2)
+		: "memory");
+}
+
+template <int BKS>
+__global__ void __launch_bounds__(CF_THREADS, 3)
+canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams p)
+{
+	using G = CFGeom<BKS>;
+	constexpr int RB = G::RB;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// 128-byte aligned base (TMA destination alignment); the pad is computed on the shared-window address so that the compiler keeps
+	// the pointers in the shared address space (LDS/STS, not generic LD/ST)
+	const unsigned int pad = (128u - (static_cast<unsigned int>(__cvta_generic_to_shared(smem_raw)) & 127u)) & 127u;
+	unsigned int* base = reinterpret_cast<unsigned int*>(smem_raw + pad);
+	// OFF_A = CF_PAD words = 16 bytes into the aligned block: shift so that sA itself is 128-byte aligned
+	unsigned int* sA = base + 32;                         // input tile rows, then blurred rows
+	unsigned int* sM = sA + (G::OFF_M - G::OFF_A);
+	unsigned int* sGw = sA + (G::OFF_G - G::OFF_A);
+	uint64_t* bar = reinterpret_cast<uint64_t*>(sA + (G::WORDS - G::OFF_A) + 2);
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int W = p.W, H = p.H;
+	const int x0 = blockIdx.x * CF_TW, y0 = blockIdx.y * CF_TH;
+	const int frame = blockIdx.z;
+	const int xl = x0 - 4 + 4 * lane;                     // first of my 4 columns
+	const int yIn0 = y0 - RB - 2;                         // image row of staged row 0
+	const int xTma = (x0 - 4) & ~15;                      // 16-byte aligned origin of the staged tile
+	const int woff = ((x0 - 4) - xTma) >> 2;              // word of lane 0 inside a staged row
+
+	// ---- S0: stage the input tile ----
+	if (p.useTma) {
+		if (threadIdx.x == 0) {
+			mbar_init(bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			mbar_expect_tx(bar, G::IN_ROWS * CF_INW * 4);
+			tma_load_3d(sA, &tmap, bar, xTma, yIn0, frame);
+		}
+		__syncthreads();
+		mbar_wait(bar, 0);
+	}
+	else {
+		const uint8_t* __restrict__ in = p.in + frame * p.framePitch;
+		for (int r = warp; r < G::IN_ROWS; r += CF_WARPS) {
+			const int y = yIn0 + r;
+			unsigned int w = 0;
+			if (y >= 0 && y < H) {
+				const uint8_t* row = in + static_cast<size_t>(y) * p.stride;
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int x = xl + i;
+					if (x >= 0 && x < W) w |= static_cast<unsigned int>(row[x]) << (8 * i);
+				}
+			}
+			sA[r * CF_INW + woff + lane] = w;
+		}
+		__syncthreads();
+	}
+
+	if (BKS) {
+		// ---- S1: horizontal blur -> sM (same rows as the input tile).  mid(y,x) = 0 outside [RB, W-RB) x [0, H) ----
+		unsigned int colMask = 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) if (xl + i >= RB && xl + i < W - RB) colMask |= 0xffu << (8 * i);
+		for (int r = warp; r < G::IN_ROWS; r += CF_WARPS) {
+			const int y = yIn0 + r;
+			unsigned int outw = 0;
+			if (y >= 0 && y < H && colMask) {
+				const unsigned int* q = &sA[r * CF_INW + woff + lane];
+				const unsigned int wl = q[-1], wc = q[0], wr = q[1];
+				float v[4 + 2 * RB];
+#pragma unroll
+				for (int j = 0; j < RB; ++j) v[j] = u8_to_f32(wl, 4 - RB + j);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) v[RB + j] = u8_to_f32(wc, j);
+#pragma unroll
+				for (int j = 0; j < RB; ++j) v[RB + 4 + j] = u8_to_f32(wr, j);
+				unsigned int o[4];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					float s = 0.f;
+#pragma unroll
+					for (int k = 0; k < BKS; ++k) s = __fmaf_rn(v[i + k], p.k[k], s);
+					o[i] = f32_to_u8_bits(s);
+				}
+				outw = pack4(o[0], o[1], o[2], o[3]) & colMask;
+			}
+			sM[r * CF_ROWW + lane] = outw;
+		}
+		__syncthreads();
+
+		// ---- S2: vertical blur -> sA (blurred rows: image y0-2 .. y0+TH+1).  B(y,x) = 0 outside [RB, H-RB) ----
+		{
+			constexpr int RPW = G::B_ROWS / CF_WARPS; // 8 rows per warp
+			static_assert(G::B_ROWS % CF_WARPS == 0, "B_ROWS must split evenly across warps");
+			const int rb0 = warp * RPW;
+			float win[RPW + 2 * RB][4];
+#pragma unroll
+			for (int r = 0; r < RPW + 2 * RB; ++r) {
+				const unsigned int w = sM[(rb0 + r) * CF_ROWW + lane];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) win[r][i] = u8_to_f32(w, i);
+			}
+			// all warps must finish READING sM... they read sM and write sA (the dead input tile): but other warps may still read sA in S1?
+			// No: S1 finished for every warp at the barrier above.
+#pragma unroll
+			for (int j = 0; j < RPW; ++j) {
+				const int y = y0 - 2 + rb0 + j;
+				unsigned int outw = 0;
+				if (y >= RB && y < H - RB) {
+					unsigned int o[4];
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						float s = 0.f;
+#pragma unroll
+						for (int k = 0; k < BKS; ++k) s = __fmaf_rn(win[j + k][i], p.k[k], s);
+						o[i] = f32_to_u8_bits(s);
+					}
+					outw = pack4(o[0], o[1], o[2], o[3]);
+				}
+				sA[(rb0 + j) * CF_ROWW + lane] = outw;
+			}
+		}
+		__syncthreads();
+	}
+	// here sA rows hold the image the gradient runs on: row rb <-> image y0-2+rb, lane word <-> columns xl..xl+3
+
+	// ---- S3: Sobel 3x3 + L1 magnitude + direction code -> sG ----
+	int tLow = p.tLow, tHigh = p.tHigh;
+	if (p.thr) { const ushort2 t = p.thr[frame]; tLow = t.x; tHigh = t.y; }
+	{
+		constexpr int RPW = (G::G_ROWS + CF_WARPS - 1) / CF_WARPS; // 8
+		const int rg0 = warp * RPW;
+		// per source row: hs[i] = p[i-1] + 2p[i] + p[i+1], hd[i] = p[i+1] - p[i-1]
+		int hs[3][4], hd[3][4];
+		// the gradient source is the blurred tile (pitch 32, word = lane) or, without blur, the staged input itself (pitch 36, word = woff+lane)
+		const int srcPitch = BKS ? CF_ROWW : CF_INW;
+		const unsigned int* src = sA + (BKS ? 0 : woff) + lane;
+		auto loadRow = [&](int rb, int slot) {
+			const unsigned int* sw = src + rb * srcPitch;
+			const unsigned int wl = sw[-1], wc = sw[0], wr = sw[1];
+			int q[6];
+			q[0] = static_cast<int>(wl >> 24);
+			q[1] = static_cast<int>(wc & 0xff); q[2] = static_cast<int>((wc >> 8) & 0xff); q[3] = static_cast<int>((wc >> 16) & 0xff); q[4] = static_cast<int>(wc >> 24);
+			q[5] = static_cast<int>(wr & 0xff);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) { hs[slot][i] = q[i] + 2 * q[i + 1] + q[i + 2]; hd[slot][i] = q[i + 2] - q[i]; }
+		};
+		loadRow(rg0, 0);
+		loadRow(rg0 + 1, 1);
+#pragma unroll
+		for (int j = 0; j < RPW; ++j) {
+			const int rg = rg0 + j;
+			if (rg < G::G_ROWS) { // warp-uniform
+				loadRow(rg + 2, (j + 2) % 3);
+				const int a = j % 3, b = (j + 1) % 3, c = (j + 2) % 3;
+				const int y = y0 - 1 + rg;
+				const bool rowOk = (y >= 1 && y < H - 1);
+				unsigned int packed[4];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int x = xl + i;
+					int gx = hd[a][i] + 2 * hd[b][i] + hd[c][i];
+					int gy = hs[c][i] - hs[a][i];
+					if (!(rowOk && x >= 1 && x < W - 1)) { gx = 0; gy = 0; }
+					const int ax = abs(gx), ay = abs(gy);
+					const int g = ax + ay;
+					unsigned int dir = 0;
+					if (g > tLow) {
+						const int ays = ay << 16;
+						if (ays < kTangentPiOver8Int * ax) dir = 0;
+						else if (ays < kTangentPiTimes3Over8Int * ax) dir = ((gx ^ gy) < 0) ? 2u : 1u;
+						else dir = 3;
+					}
+					packed[i] = static_cast<unsigned int>(g) | (dir << 14);
+				}
+				uint2 o;
+				o.x = packed[0] | (packed[1] << 16);
+				o.y = packed[2] | (packed[3] << 16);
+				*reinterpret_cast<uint2*>(&sGw[rg * 64 + lane * 2]) = o;
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- S4: NMS on the unsuppressed g + classification -> global ----
+	{
+		const unsigned short* sG = reinterpret_cast<const unsigned short*>(sGw);
+		uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
+		const bool laneOut = (lane >= 1 && lane <= 30);
+		for (int ro = warp; ro < CF_TH; ro += CF_WARPS) {
+			const int y = y0 + ro;
+			if (y >= H) break; // warp-uniform
+			const int rg = ro + 1;
+			if (!laneOut || xl >= W) continue;
+			const uint2 gw = *reinterpret_cast<const uint2*>(&sGw[rg * 64 + lane * 2]);
+			unsigned int outw = 0;
+			const unsigned int g4[4] = { gw.x & 0xffffu, gw.x >> 16, gw.y & 0xffffu, gw.y >> 16 };
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int gc = static_cast<int>(g4[i] & 0x3fffu);
+				if (gc > tLow) {
+					const unsigned int dir = g4[i] >> 14;
+					const int idx = rg * 128 + lane * 4 + i;
+					const int off = (dir == 0) ? 1 : (dir == 1) ? 129 : (dir == 2) ? -127 : 128;
+					const int n0 = sG[idx - off] & 0x3fff, n1 = sG[idx + off] & 0x3fff;
+					if (!(n0 > gc || n1 > gc)) outw |= static_cast<unsigned int>(gc > tHigh ? CLS_STRONG : CLS_WEAK) << (8 * i);
+				}
+			}
+			uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
+			if (p.vecStore && xl + 4 <= W) {
+				*reinterpret_cast<unsigned int*>(o) = outw;
+			}
+			else {
+#pragma unroll
+				for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+			}
+		}
+	}
+}
+
+// ---- host side: tensor map + launch ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+	CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled()
+{
+	static PFN_encodeTiled fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+		else cudaGetLastError();
+	}
+	return fn;
+}
+
+// u8 frames as a 3-D tensor {W, H, batch} with byte strides {stride, framePitch}; box = {144, rows, 1}
+static bool make_u8_tile_map(CUtensorMap* map, const uint8_t* base, size_t W, size_t H, size_t stride, size_t framePitch, size_t batch, int boxRows)
+{
+	PFN_encodeTiled enc = get_encode_tiled();
+	if (!enc) return false;
+	if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride & 15) || (framePitch & 15)) return false;
+	const cuuint64_t dims[3] = { W, H, batch };
+	const cuuint64_t strides[2] = { stride, framePitch };
+	const cuuint32_t box[3] = { CF_INW * 4, static_cast<cuuint32_t>(boxRows), 1 };
+	const cuuint32_t estr[3] = { 1, 1, 1 };
+	return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+		CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BKS>
+static int launch_canny_fast_t(const FastParams& p0, size_t batch, cudaStream_t stream)
+{
+	using G = CFGeom<BKS>;
+	FastParams p = p0;
+	alignas(64) CUtensorMap map;
+	memset(&map, 0, sizeof(map));
+	p.useTma = make_u8_tile_map(&map, p.in, p.W, p.H, p.stride, p.framePitch, batch, G::IN_ROWS) ? 1 : 0;
+	p.vecStore = (((reinterpret_cast<uintptr_t>(p.cls) | p.stride | p.framePitch) & 3) == 0) ? 1 : 0;
+	auto kern = canny_front_fast_kernel<BKS>;
+	static bool attrSet = false;
+	if (!attrSet) {
+		CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)));
+		attrSet = true;
+	}
+	dim3 grid(static_cast<unsigned>(div_up(p.W, CF_TW)), static_cast<unsigned>(div_up(p.H, CF_TH)), static_cast<unsigned>(batch));
+	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
+	{
+		KernelScope ks_("canny_front", stream);
+		kern<<<grid, CF_THREADS, G::SMEM, stream>>>(map, p);
+	}
+	CVB_LAUNCHED();
+	return CVB200_S_OK;
+}
+
+} // namespace cvb

@@ -474,6 +474,8 @@ static int launch_front(const FrontParams& p, int mode, size_t batch, cudaStream
 
 } // namespace cvb
 
+#include "canny_fast.cuh"
+
 using namespace cvb;
 
 // The detector object: caches its scratch like the reference objects do (canny_dete.cxx:133-147)
@@ -488,6 +490,7 @@ struct cvb200_edge_dete {
 	HostBuf hostFlag;
 	DevBuf hostIn, hostOut; // staging for the host-buffer entry point
 	bool gmaxLanes;
+	bool genericKernel;     // CVB200_EDGE_SET_BOOL_GENERIC_KERNEL: force the generic front kernel (tests)
 	std::mutex mutex;
 };
 
@@ -509,6 +512,7 @@ int cvb200_edge_dete_new(cvb200_edge_dete_t** dete, int id, float tLow, float tH
 	d->thresholdType = CVB200_CANNY_THRESHOLD_TYPE_COMPARE_TO_GRADIENT;
 	d->taps = taps;
 	d->gmaxLanes = false;
+	d->genericKernel = false;
 	memset(&d->blur, 0, sizeof(d->blur));
 	*dete = d;
 	return CVB200_S_OK;
@@ -529,6 +533,11 @@ int cvb200_edge_dete_free(cvb200_edge_dete_t** dete)
 int cvb200_edge_dete_set(cvb200_edge_dete_t* d, int id, const void* valuePtr, size_t valueSize)
 {
 	CVB_REQUIRE(d && valuePtr && valueSize, CVB200_E_INVALID_PARAMETER);
+	if (id == CVB200_EDGE_SET_BOOL_GENERIC_KERNEL) {
+		CVB_REQUIRE(valueSize == sizeof(bool), CVB200_E_INVALID_PARAMETER);
+		d->genericKernel = *static_cast<const bool*>(valuePtr);
+		return CVB200_S_OK;
+	}
 	if (id == CVB200_EDGE_SET_BOOL_X86_SSE41_GMAX_LANES) {
 		CVB_REQUIRE(valueSize == sizeof(bool) && d->id != CVB200_CANNY_ID, CVB200_E_INVALID_PARAMETER);
 		d->gmaxLanes = *static_cast<const bool*>(valuePtr);
@@ -651,7 +660,21 @@ int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, si
 		p.tLow = tLow; p.tHigh = tHigh;
 	}
 
-	CVB_CHECK(launch_front(p, 0, batch, stream));
+	if (!d->genericKernel && p.taps.ks == 3 && (p.blur.ks == 0 || p.blur.ks == 3 || p.blur.ks == 5)) {
+		// fast path (canny_fast.cuh): TMA-staged tile, 4 px per lane
+		FastParams f;
+		memset(&f, 0, sizeof(f));
+		f.in = image; f.cls = edges; f.thr = p.thr;
+		f.W = p.W; f.H = p.H; f.stride = stride; f.framePitch = framePitch;
+		f.tLow = p.tLow; f.tHigh = p.tHigh;
+		for (int i = 0; i < p.blur.ks; ++i) f.k[i] = p.blur.k[i];
+		if (p.blur.ks == 0) CVB_CHECK(launch_canny_fast_t<0>(f, batch, stream));
+		else if (p.blur.ks == 3) CVB_CHECK(launch_canny_fast_t<3>(f, batch, stream));
+		else CVB_CHECK(launch_canny_fast_t<5>(f, batch, stream));
+	}
+	else {
+		CVB_CHECK(launch_front(p, 0, batch, stream));
+	}
 
 	// hysteresis rounds. Round 0 visits every tile; later rounds only tiles flagged dirty. Rounds are issued in groups of 4 without host
 	// interaction (a round with nothing dirty costs one empty launch); the host reads the last counter of a group to decide whether to go on.

@@ -96,6 +96,9 @@ extern "C" {
  * i.e. the reference's plain C++ path (compv_math_utils.h:158-170). */
 #define CVB200_EDGE_SET_BOOL_X86_SSE41_GMAX_LANES       1000
 
+/* Extension, bool: force the generic (any kernel size / any stride) Canny front kernel instead of the TMA fast path. Test hook. */
+#define CVB200_EDGE_SET_BOOL_GENERIC_KERNEL             1001
+
 /* COMPV_BORDER_TYPE (compv_common.h) */
 #define CVB200_BORDER_TYPE_ZERO      0
 #define CVB200_BORDER_TYPE_IGNORE    1

@@ -98,9 +98,22 @@ def test_canny(ks, tlow, thigh, w, h, stride):
         # When (W-1) % 16 == 0 the reference's AVX2 NMS / SSE2 hysteresis leaves skip the last 15 columns and no scalar tail runs
         # (canny_dete.cxx:396,514: colStart = (W-1) & -15 == W-1), so its SIMD path disagrees with its own C++ path; the C++ path is the spec.
         simd = ((w - 1) % 16) != 0
-        for threads in (1, -1):  # the reference's own invariant: thread count does not change the bytes
-            b = oracle.edge_dete("ref", img, "canny", tlow, thigh, ks, width=w, threads=threads, simd=simd)
-            np.testing.assert_array_equal(a[:, :w], b[:, :w])
+        b = oracle.edge_dete("ref", img, "canny", tlow, thigh, ks, width=w, threads=1, simd=simd)
+        np.testing.assert_array_equal(a[:, :w], b[:, :w])
+
+
+@needs_ref
+def test_canny_reference_mt_is_a_subset():
+    """The reference's multi-threaded hysteresis lets strips write the shared edge map concurrently (canny_dete.cxx:282-306) with
+    vector-wide read-modify-write stores (intrin/x86/...canny_dete_intrin_sse2.cxx:107-197): on a many-core host marks can be lost
+    (observed on a 128-core box: 44 of 3072 pixels on the 64x48 uniform frame), so its MT output is not deterministic.  What always holds
+    is that MT marks a subset of the single-threaded closure, which is what the oracle (and the CUDA path) compute."""
+    for (w, h, stride) in [(64, 48, 64), (640, 480, 640)]:
+        for img in _frames(w, h, stride):
+            st = oracle.edge_dete("orc", img, "canny", 59.0, 119.0, 3, width=w)
+            mt = oracle.edge_dete("ref", img, "canny", 59.0, 119.0, 3, width=w, threads=-1)
+            assert not np.any((mt[:, :w] == 255) & (st[:, :w] == 0))
+            assert (mt[:, :w] != st[:, :w]).mean() < 0.05
 
 
 @needs_ref
