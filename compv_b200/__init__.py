@@ -142,3 +142,57 @@ class CompVEdgeDete:
                 lib().cvb200_edge_dete_free(C.byref(self._h))
         except Exception:
             pass
+
+
+# ---- a8: CompVCornerDete (FAST) --------------------------------------------------------------------
+POINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("strength", np.float32), ("orient", np.float32), ("level", np.int32), ("size", np.float32)])
+
+
+def fast_scores(img, N=9, threshold=20, width=None):
+    """K11 strength map through cvb200_fast_scores (shape of the reference's GPU hook processData)."""
+    w, h, stride = _frame(img, width)
+    out = np.zeros((h, stride), np.uint8)
+    check(lib().cvb200_fast_scores(vp(img), sz(w), sz(h), sz(stride), int(N), int(threshold), vp(out)), "cvb200_fast_scores")
+    return out
+
+
+class CompVCornerDete:
+    """Mirror of CompVCornerDete (base/include/compv/base/compv_features.h:166-174) over cvb200_corner_dete_*."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def newObj(dete_id=FAST_ID):
+        h = C.c_void_p()
+        check(lib().cvb200_corner_dete_new(C.byref(h), int(dete_id)), "cvb200_corner_dete_new")
+        return CompVCornerDete(h)
+
+    def set(self, cap_id, value, ctype):
+        v = ctype(value)
+        return lib().cvb200_corner_dete_set(self._h, int(cap_id), C.byref(v), sz(C.sizeof(v)))
+
+    def setInt(self, cap_id, value):
+        check(self.set(cap_id, value, C.c_int32), "cvb200_corner_dete_set")
+
+    def setBool(self, cap_id, value):
+        check(self.set(cap_id, bool(value), C.c_bool), "cvb200_corner_dete_set")
+
+    def process(self, image, width=None, capacity=None):
+        w, h, stride = _frame(image, width)
+        cap = int(capacity if capacity is not None else w * h)
+        pts = np.zeros(max(cap, 1), POINT_DTYPE)
+        cnt = C.c_size_t(0)
+        check(lib().cvb200_corner_dete_process(self._h, vp(image), sz(w), sz(h), sz(stride), vp(pts), sz(cap), C.byref(cnt)), "cvb200_corner_dete_process")
+        return pts[:min(cnt.value, cap)].copy()
+
+    def process_dev(self, d_image, width, height, stride, d_points, capacity, d_counts, batch=1, frame_pitch=0, stream=0):
+        check(lib().cvb200_corner_dete_process_dev(self._h, vp(d_image), sz(width), sz(height), sz(stride), vp(d_points), sz(capacity), vp(d_counts), sz(batch),
+                                                   sz(frame_pitch), C.c_void_p(stream)), "cvb200_corner_dete_process_dev")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cvb200_corner_dete_free(C.byref(self._h))
+        except Exception:
+            pass

@@ -10,7 +10,7 @@
 // output on [x0, x0+120) (lanes 1..30).  120 divides 1920 and 3840, 60 divides 1080, 2160 and 480.
 #pragma once
 
-#include <cuda.h>
+#include "tma.cuh"
 
 namespace cvb {
 
@@ -52,41 +52,16 @@ __device__ __forceinline__ float u8_to_f32(unsigned int w, int byteIdx)
 	return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | byteIdx)) - 8388608.f;
 }
 
-// trunc(clamp(s, 0, 255)) in the low byte of the returned bit pattern (2^23 magic add, round toward zero)
+// trunc(s) in the low byte of the returned bit pattern (2^23 magic add, round toward zero).  Valid for 0 <= s < 256: the fast path is only
+// taken for non-negative taps whose sum is <= 1.003 (a normalised Gaussian), so s <= 255 * 1.003 < 256 and the reference's clamp is a no-op.
 __device__ __forceinline__ unsigned int f32_to_u8_bits(float s)
 {
-	s = fminf(fmaxf(s, 0.f), 255.f);
 	return __float_as_uint(__fadd_rz(s, 8388608.f));
 }
 
 __device__ __forceinline__ unsigned int pack4(unsigned int a, unsigned int b, unsigned int c, unsigned int d)
 {
 	return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase)
-{
-	const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
-	unsigned ok;
-	do {
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(phase) : "memory");
-	} while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void* smemDst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
-{
-	asm volatile(
-		"cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-		:: "r"(static_cast<unsigned>(__cvta_generic_to_shared(smemDst))), "l"(reinterpret_cast<uint64_t>(map)),
-		   "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(c0), "r"(c1), "r"(c2)
-		: "memory");
 }
 
 template <int BKS>
@@ -306,38 +281,7 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 	}
 }
 
-// ---- host side: tensor map + launch ----
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-	CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_tiled()
-{
-	static PFN_encodeTiled fn = nullptr;
-	static bool tried = false;
-	if (!tried) {
-		tried = true;
-		void* p = nullptr;
-		cudaDriverEntryPointQueryResult qres;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
-		else cudaGetLastError();
-	}
-	return fn;
-}
-
-// u8 frames as a 3-D tensor {W, H, batch} with byte strides {stride, framePitch}; box = {144, rows, 1}
-static bool make_u8_tile_map(CUtensorMap* map, const uint8_t* base, size_t W, size_t H, size_t stride, size_t framePitch, size_t batch, int boxRows)
-{
-	PFN_encodeTiled enc = get_encode_tiled();
-	if (!enc) return false;
-	if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride & 15) || (framePitch & 15)) return false;
-	const cuuint64_t dims[3] = { W, H, batch };
-	const cuuint64_t strides[2] = { stride, framePitch };
-	const cuuint32_t box[3] = { CF_INW * 4, static_cast<cuuint32_t>(boxRows), 1 };
-	const cuuint32_t estr[3] = { 1, 1, 1 };
-	return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-		CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
+// ---- host side: launch ----
 template <int BKS>
 static int launch_canny_fast_t(const FastParams& p0, size_t batch, cudaStream_t stream)
 {
@@ -345,7 +289,7 @@ static int launch_canny_fast_t(const FastParams& p0, size_t batch, cudaStream_t 
 	FastParams p = p0;
 	alignas(64) CUtensorMap map;
 	memset(&map, 0, sizeof(map));
-	p.useTma = make_u8_tile_map(&map, p.in, p.W, p.H, p.stride, p.framePitch, batch, G::IN_ROWS) ? 1 : 0;
+	p.useTma = make_u8_tile_map(&map, p.in, p.W, p.H, p.stride, p.framePitch, batch, CF_INW * 4, G::IN_ROWS) ? 1 : 0;
 	p.vecStore = (((reinterpret_cast<uintptr_t>(p.cls) | p.stride | p.framePitch) & 3) == 0) ? 1 : 0;
 	auto kern = canny_front_fast_kernel<BKS>;
 	static bool attrSet = false;

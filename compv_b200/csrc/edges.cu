@@ -660,7 +660,13 @@ int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, si
 		p.tLow = tLow; p.tHigh = tHigh;
 	}
 
-	if (!d->genericKernel && p.taps.ks == 3 && (p.blur.ks == 0 || p.blur.ks == 3 || p.blur.ks == 5)) {
+	bool tapsOk = true; // the fast path drops the (then redundant) 0..255 clamp of the blur: needs non-negative taps summing to <= 1.003
+	{
+		float sum = 0.f;
+		for (int i = 0; i < p.blur.ks; ++i) { if (!(p.blur.k[i] >= 0.f)) tapsOk = false; sum += p.blur.k[i]; }
+		if (!(sum <= 1.003f)) tapsOk = false;
+	}
+	if (!d->genericKernel && tapsOk && p.taps.ks == 3 && (p.blur.ks == 0 || p.blur.ks == 3 || p.blur.ks == 5)) {
 		// fast path (canny_fast.cuh): TMA-staged tile, 4 px per lane
 		FastParams f;
 		memset(&f, 0, sizeof(f));

@@ -1,0 +1,496 @@
+// a8 -- FAST9 / FAST12 corner detector: strength map (K11), 3x3 non-maximum suppression and raster-ordered point list (K12).
+// Replaces CompVCornerDeteFAST::process (core/features/fast/compv_core_feature_fast_dete.cxx:163-422), the leaves
+// CompVFastDataRow_C (:658-771), CompVFastNmsGather_C/_Apply_C (:773-831) and CompVFastBuildInterestPoints (:490-585).
+// The reference author already put the GPU seam at "produce the strength map" (CompVGpuCornerDeteFAST::processData,
+// gpu/include/compv/gpu/core/features/fast/compv_gpu_feature_fast_dete.h:23-47, call site compiled out at fast_dete.cxx:252-283);
+// cvb200_fast_scores has exactly that shape.
+//
+// One kernel per batch does the pixel work (HBM traffic: 1 B/px read + 1 bit/px mask + a few bytes per corner):
+//   stage 0  TMA tile load (u8, 144 x (TH+8) box, zero filled outside the image)
+//   stage A  compass test on 4 px per lane: a contiguous arc of N>=9 of the 16 circle pixels always contains at least
+//            2 (N=9) / 3 (N=12) of the 4 compass pixels, so "fewer than that are darker and fewer are brighter" rejects exactly;
+//            survivors are compacted into a shared-memory queue with warp ballots
+//   stage B  full segment test on the queue (one candidate per thread): 16-bit darker/brighter masks, run-of-N test by shift-and,
+//            strength = max over qualifying arcs of the minimum |difference| in the arc; written to a shared strength tile
+//   stage C  NMS (suppressed when any 8-neighbour is >= own strength, ties kill both) and emission: a bit in the per-frame corner
+//            mask (atomicOr) + (key,strength) appended to an unordered list
+// then   fast_rank_prefix: exclusive scan of the popcounts of the mask words (one block per frame)
+//        fast_emit_points: every list entry finds its raster rank = prefix[word] + popc(lower bits) and writes its point there.
+#include "common.cuh"
+#include "tma.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace cvb {
+
+constexpr int FA_TW = 120, FA_TH = 56, FA_THREADS = 256, FA_WARPS = 8;
+constexpr int FA_INW = 36;                 // words per staged row (144-byte TMA box, see canny_fast.cuh)
+constexpr int FA_IN_ROWS = FA_TH + 8;      // image rows y0-4 .. y0+TH+3
+constexpr int FA_S_ROWS = FA_TH + 2;       // strength rows y0-1 .. y0+TH
+constexpr int FA_S_PITCH = 128;            // strength tile: one byte per staged column
+constexpr int FA_QCAP = FA_S_ROWS * 122;   // every pixel of the strength region may be a candidate
+
+struct FastKParams {
+	const uint8_t* in;
+	uint8_t* scores;            // optional dense strength map (cvb200_fast_scores); pre-NMS values, 0 elsewhere
+	unsigned int* mask;         // [batch][maskWordsPerFrame] corner bits (nullptr when only scores are wanted)
+	unsigned long long* list;   // [batch][listCap] (key << 8) | strength
+	unsigned int* listCount;    // [batch]
+	int W, H;
+	size_t stride, framePitch;
+	int threshold, N, nms;
+	int useTma;
+	unsigned int maskWordsPerFrame, listCap;
+};
+
+// circle offsets (dx, dy) in the reference's order (fast_dete.cxx:221-238)
+__constant__ int c_circle_dx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
+__constant__ int c_circle_dy[16] = { -3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3 };
+
+// bit i of the result is set when bits i..i+n-1 (circularly, 16 positions) of m are all set
+__device__ __forceinline__ unsigned int arc_starts(unsigned int m, int n)
+{
+	const unsigned int x = m | (m << 16);
+	unsigned int a = x & (x >> 1);   // runs >= 2
+	unsigned int b = a & (a >> 2);   // runs >= 4
+	unsigned int c = b & (b >> 4);   // runs >= 8
+	unsigned int d = (n == 9) ? (c & (x >> 8)) : (c & (b >> 8)); // 8+1, or 8 followed by 4 starting at +8 = 12
+	return d & 0xffffu;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 3)
+fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const unsigned int pad = (128u - (static_cast<unsigned int>(__cvta_generic_to_shared(smem_raw)) & 127u)) & 127u;
+	unsigned int* sIn = reinterpret_cast<unsigned int*>(smem_raw + pad) + 32;           // FA_IN_ROWS x FA_INW words (128-byte aligned, 32 pad words in front)
+	uint8_t* sS = reinterpret_cast<uint8_t*>(sIn + FA_IN_ROWS * FA_INW + 4);            // FA_S_ROWS x 128 bytes, +1 row of slack on each side
+	unsigned short* sQ = reinterpret_cast<unsigned short*>(sS + (FA_S_ROWS + 2) * FA_S_PITCH); // candidate queue
+	uint64_t* bar = reinterpret_cast<uint64_t*>(sQ + ((FA_QCAP + 3) & ~3));
+	__shared__ unsigned int sQn;
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int W = p.W, H = p.H;
+	const int x0 = blockIdx.x * FA_TW, y0 = blockIdx.y * FA_TH;
+	const int frame = blockIdx.z;
+	const int xl = x0 - 4 + 4 * lane;
+	const int yIn0 = y0 - 4;
+	const int xTma = (x0 - 4) & ~15;
+	const int woff = ((x0 - 4) - xTma) >> 2;
+	const int t = p.threshold;
+
+	if (threadIdx.x == 0) sQn = 0;
+	if (p.useTma) {
+		if (threadIdx.x == 0) {
+			mbar_init(bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			mbar_expect_tx(bar, FA_IN_ROWS * FA_INW * 4);
+			tma_load_3d(sIn, &tmap, bar, xTma, yIn0, frame);
+		}
+	}
+	else {
+		const uint8_t* __restrict__ in = p.in + frame * p.framePitch;
+		for (int r = warp; r < FA_IN_ROWS; r += FA_WARPS) {
+			const int y = yIn0 + r;
+			unsigned int w = 0;
+			if (y >= 0 && y < H) {
+				const uint8_t* row = in + static_cast<size_t>(y) * p.stride;
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int x = xl + i;
+					if (x >= 0 && x < W) w |= static_cast<unsigned int>(row[x]) << (8 * i);
+				}
+			}
+			sIn[r * FA_INW + woff + lane] = w;
+		}
+	}
+	// zero the strength tile (with its slack rows) while the copy is in flight
+	for (int i = threadIdx.x; i < (FA_S_ROWS + 2) * FA_S_PITCH / 4; i += FA_THREADS) reinterpret_cast<unsigned int*>(sS)[i] = 0;
+	__syncthreads();
+	if (p.useTma) mbar_wait(bar, 0);
+	uint8_t* sStr = sS + FA_S_PITCH; // row 0 of the strength region (image y0-1); one slack row above and below
+
+	// ---- stage A: compass test, 4 px per lane, rows of the strength region ----
+	const int need = (p.N == 12) ? 3 : 2;
+	for (int rs = warp; rs < FA_S_ROWS; rs += FA_WARPS) {
+		const int y = y0 - 1 + rs;
+		unsigned int cand = 0; // 4 bits
+		if (y >= 3 && y < H - 3) {
+			const unsigned int* q = &sIn[(rs + 3) * FA_INW + woff + lane]; // staged row of image y (yIn0 = y0-4 -> row index y - yIn0 = rs + 3)
+			const unsigned int wc = q[0], wl = q[-1], wr = q[1];
+			const unsigned int wu = q[-3 * FA_INW], wd = q[3 * FA_INW];
+			// pixel i: left = byte (i-3) of [wl wc], right = byte (i+3) of [wc wr]
+			const unsigned int wL = __byte_perm(wl, wc, 0x4321);   // bytes x-3..x   -> [wl.b1 wl.b2 wl.b3 wc.b0]
+			const unsigned int wR = __byte_perm(wc, wr, 0x6543);   // bytes x+3..x+6 -> [wc.b3 wr.b0 wr.b1 wr.b2]
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int x = xl + i;
+				const int pc = (wc >> (8 * i)) & 0xff;
+				const int br = min(pc + t, 255), dk = max(pc - t, 0);
+				const int cU = (wu >> (8 * i)) & 0xff, cD = (wd >> (8 * i)) & 0xff, cL = (wL >> (8 * i)) & 0xff, cR = (wR >> (8 * i)) & 0xff;
+				const int nd = (cU < dk) + (cD < dk) + (cL < dk) + (cR < dk);
+				const int nb = (cU > br) + (cD > br) + (cL > br) + (cR > br);
+				if ((nd >= need || nb >= need) && x >= 3 && x < W - 3 && x >= x0 - 1 && x <= x0 + FA_TW) cand |= 1u << i;
+			}
+		}
+		// warp-ballot compaction into the queue (order inside the queue is irrelevant)
+		const unsigned int any = __ballot_sync(0xffffffffu, cand != 0);
+		if (any) {
+			const int cnt = __popc(cand);
+			int incl = cnt;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+			const int total = __shfl_sync(0xffffffffu, incl, 31);
+			unsigned int base = 0;
+			if (lane == 0) base = atomicAdd(&sQn, static_cast<unsigned int>(total));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			unsigned int pos = base + incl - cnt;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) if (cand & (1u << i)) sQ[pos++] = static_cast<unsigned short>(rs * FA_S_PITCH + lane * 4 + i);
+		}
+	}
+	__syncthreads();
+
+	// ---- stage B: full segment test on the candidates ----
+	const unsigned int qn = sQn;
+	const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn) + woff * 4; // byte (r, c): column c <-> image x0-4+c
+	for (unsigned int qi = threadIdx.x; qi < qn; qi += FA_THREADS) {
+		const int code = sQ[qi];
+		const int rs = code >> 7, c = code & 127;
+		const uint8_t* ctr = sInB + (rs + 3) * (FA_INW * 4) + c;
+		const int pc = ctr[0];
+		const int br = min(pc + t, 255), dk = max(pc - t, 0);
+		unsigned long long vlo = 0, vhi = 0; // the 16 circle bytes, k = 0..7 in vlo, 8..15 in vhi (registers, no local-memory array)
+		unsigned int md = 0, mb = 0;
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			const int vk = ctr[c_circle_dy[k] * (FA_INW * 4) + c_circle_dx[k]];
+			if (k < 8) vlo |= static_cast<unsigned long long>(vk) << (8 * k); else vhi |= static_cast<unsigned long long>(vk) << (8 * (k - 8));
+			md |= (vk < dk ? 1u : 0u) << k;
+			mb |= (vk > br ? 1u : 0u) << k;
+		}
+		int strength = 0;
+		// fast_dete.cxx:733-764: darker arcs when >= N pixels are darker, else brighter arcs when >= N are brighter
+		unsigned int starts = 0;
+		bool dark = false;
+		if (__popc(md) >= p.N) { starts = arc_starts(md, p.N); dark = true; }
+		else if (__popc(mb) >= p.N) { starts = arc_starts(mb, p.N); }
+		while (starts) {
+			const int s = __ffs(starts) - 1;
+			starts &= starts - 1;
+			int mn = 255;
+			for (int k = 0; k < p.N; ++k) {
+				const int idx = (s + k) & 15;
+				const int val = static_cast<int>(((idx < 8 ? vlo : vhi) >> (8 * (idx & 7))) & 0xff);
+				const int dif = dark ? (dk - val) : (val - br);
+				mn = min(mn, dif);
+			}
+			strength = max(strength, mn);
+		}
+		if (strength) sStr[rs * FA_S_PITCH + c] = static_cast<uint8_t>(strength);
+	}
+	__syncthreads();
+
+	// ---- stage C: NMS + emission, output rows y0 .. y0+TH-1 (strength rows 1..TH), lanes 1..30 ----
+	const bool laneOut = (lane >= 1 && lane <= 30);
+	for (int ro = warp; ro < FA_TH; ro += FA_WARPS) {
+		const int y = y0 + ro;
+		if (y >= H) break;
+		const int rs = ro + 1;
+		const unsigned int sw = *reinterpret_cast<const unsigned int*>(&sStr[rs * FA_S_PITCH + lane * 4]);
+		if (p.scores && laneOut && xl < W) {
+			uint8_t* o = p.scores + frame * p.framePitch + static_cast<size_t>(y) * p.stride + xl;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(sw >> (8 * i));
+		}
+		if (!p.mask || !laneOut || !sw) continue;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const int s = (sw >> (8 * i)) & 0xff;
+			if (!s) continue;
+			const int x = xl + i;
+			if (p.nms) {
+				const uint8_t* q = &sStr[rs * FA_S_PITCH + lane * 4 + i];
+				// fast_dete.cxx:773-812: suppressed when ANY of the 8 neighbours is >= own strength
+				if (q[-1] >= s || q[1] >= s || q[-FA_S_PITCH - 1] >= s || q[-FA_S_PITCH] >= s || q[-FA_S_PITCH + 1] >= s
+					|| q[FA_S_PITCH - 1] >= s || q[FA_S_PITCH] >= s || q[FA_S_PITCH + 1] >= s) continue;
+			}
+			const unsigned int key = static_cast<unsigned int>(y) * static_cast<unsigned int>(W) + static_cast<unsigned int>(x);
+			atomicOr(&p.mask[frame * static_cast<size_t>(p.maskWordsPerFrame) + (key >> 5)], 1u << (key & 31));
+			const unsigned int slot = atomicAdd(&p.listCount[frame], 1u);
+			if (slot < p.listCap) p.list[frame * static_cast<size_t>(p.listCap) + slot] = (static_cast<unsigned long long>(key) << 8) | static_cast<unsigned long long>(s);
+		}
+	}
+}
+
+// exclusive prefix of popc(mask word) per frame; one block per frame, 1024 threads
+__global__ void __launch_bounds__(1024)
+fast_rank_prefix_kernel(const unsigned int* mask, unsigned int* prefix, unsigned int wordsPerFrame)
+{
+	__shared__ unsigned int sWarp[32];
+	__shared__ unsigned int sCarry;
+	const unsigned int* m = mask + blockIdx.x * static_cast<size_t>(wordsPerFrame);
+	unsigned int* out = prefix + blockIdx.x * static_cast<size_t>(wordsPerFrame);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) sCarry = 0;
+	__syncthreads();
+	for (unsigned int base = 0; base < wordsPerFrame; base += 1024) {
+		const unsigned int i = base + threadIdx.x;
+		const unsigned int c = (i < wordsPerFrame) ? __popc(m[i]) : 0;
+		unsigned int incl = c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+		if (lane == 31) sWarp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			unsigned int w = sWarp[lane];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+			sWarp[lane] = w; // inclusive over warps
+		}
+		__syncthreads();
+		const unsigned int carry = sCarry;
+		const unsigned int warpBase = warp ? sWarp[warp - 1] : 0;
+		if (i < wordsPerFrame) out[i] = carry + warpBase + incl - c;
+		__syncthreads();
+		if (threadIdx.x == 0) sCarry = carry + sWarp[31];
+		__syncthreads();
+	}
+}
+
+// CompVInterestPoint layout (base/include/compv/base/compv_common.h:629-656)
+__global__ void fast_emit_points_kernel(const unsigned long long* list, const unsigned int* listCount, unsigned int listCap, const unsigned int* mask,
+	const unsigned int* prefix, unsigned int wordsPerFrame, int W, int thresholdMinus1, cvb200_interest_point_t* points, unsigned int capacity, unsigned int* counts)
+{
+	const int frame = blockIdx.y;
+	const unsigned int n = min(listCount[frame], listCap);
+	if (blockIdx.x == 0 && threadIdx.x == 0) counts[frame] = listCount[frame];
+	for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned long long e = list[frame * static_cast<size_t>(listCap) + i];
+		const unsigned int key = static_cast<unsigned int>(e >> 8), s = static_cast<unsigned int>(e & 0xff);
+		const unsigned int word = key >> 5, bit = key & 31;
+		const unsigned int rank = prefix[frame * static_cast<size_t>(wordsPerFrame) + word] + __popc(mask[frame * static_cast<size_t>(wordsPerFrame) + word] & ((1u << bit) - 1u));
+		if (rank >= capacity) continue;
+		cvb200_interest_point_t pt;
+		pt.x = static_cast<float>(key % static_cast<unsigned int>(W));
+		pt.y = static_cast<float>(key / static_cast<unsigned int>(W));
+		pt.strength = static_cast<float>(s + thresholdMinus1); // fast_dete.cxx:515-519: strength + (threshold - 1)
+		pt.orient = -1.f; pt.level = 0; pt.size = 0.f;           // CompVInterestPoint ctor defaults
+		points[frame * static_cast<size_t>(capacity) + rank] = pt;
+	}
+}
+
+constexpr size_t FA_SMEM = 128 + 128 + (FA_IN_ROWS * FA_INW + 4) * 4 + (FA_S_ROWS + 2) * FA_S_PITCH + ((FA_QCAP + 3) & ~3) * 2 + 16;
+
+} // namespace cvb
+
+using namespace cvb;
+
+struct cvb200_corner_dete {
+	int id;
+	int threshold;       // COMPV_FEATURE_DETE_FAST_THRESHOLD_DEFAULT 20
+	int type;            // FAST_TYPE_9
+	int N;
+	int maxFeatures;     // 2000
+	bool nms;            // true
+	DevBuf mask, prefix, list, counters, hostIn, points;
+	HostBuf hostCount;
+	std::mutex mutex;
+};
+
+static int fast_launch(cvb200_corner_dete* d, const uint8_t* image, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
+	uint8_t* scores, cvb200_interest_point_t* points, size_t capacity, unsigned int* counts, int threshold, int N, bool nms, cudaStream_t stream)
+{
+	CVB_REQUIRE(width >= 4 && height >= 4, CVB200_E_INVALID_PARAMETER); // fast_dete.cxx:181
+	CVB_REQUIRE(width * height < (1ull << 32) && width <= 0x3fffffff && height <= 0x3fffffff, CVB200_E_OUT_OF_BOUND);
+	FastKParams p;
+	memset(&p, 0, sizeof(p));
+	p.in = image; p.scores = scores;
+	p.W = static_cast<int>(width); p.H = static_cast<int>(height);
+	p.stride = stride; p.framePitch = framePitch;
+	p.threshold = threshold; p.N = N; p.nms = nms ? 1 : 0;
+	const unsigned int words = static_cast<unsigned int>(div_up(width * height, 32));
+	p.maskWordsPerFrame = words;
+	if (points) {
+		size_t cap = (width * height) / 4 + 1024;     // entries per frame; NMS'd corners are never 8-adjacent (<= W*H/4), without NMS every pixel may score
+		if (!nms) cap = width * height;
+		CVB_REQUIRE(cap < (1ull << 32), CVB200_E_OUT_OF_BOUND);
+		p.listCap = static_cast<unsigned int>(cap);
+		CVB_CHECK(d->mask.ensure(batch * words * sizeof(unsigned int)));
+		CVB_CHECK(d->prefix.ensure(batch * words * sizeof(unsigned int)));
+		CVB_CHECK(d->list.ensure(batch * cap * sizeof(unsigned long long)));
+		CVB_CHECK(d->counters.ensure(batch * sizeof(unsigned int)));
+		p.mask = d->mask.as<unsigned int>();
+		p.list = d->list.as<unsigned long long>();
+		p.listCount = d->counters.as<unsigned int>();
+		CVB_CUDA(cudaMemsetAsync(p.mask, 0, batch * words * sizeof(unsigned int), stream));
+		CVB_CUDA(cudaMemsetAsync(p.listCount, 0, batch * sizeof(unsigned int), stream));
+	}
+	alignas(64) CUtensorMap map;
+	memset(&map, 0, sizeof(map));
+	p.useTma = make_u8_tile_map(&map, image, width, height, stride, framePitch, batch, FA_INW * 4, FA_IN_ROWS) ? 1 : 0;
+	static bool attrSet = false;
+	if (!attrSet) { CVB_CUDA(cudaFuncSetAttribute(fast_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(FA_SMEM))); attrSet = true; }
+	dim3 grid(static_cast<unsigned>(div_up(width, FA_TW)), static_cast<unsigned>(div_up(height, FA_TH)), static_cast<unsigned>(batch));
+	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
+	{
+		KernelScope ks_("fast_detect", stream);
+		fast_detect_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(map, p);
+	}
+	CVB_LAUNCHED();
+	if (points) {
+		{
+			KernelScope ks_("fast_rank_prefix", stream);
+			fast_rank_prefix_kernel<<<static_cast<unsigned>(batch), 1024, 0, stream>>>(p.mask, d->prefix.as<unsigned int>(), words);
+		}
+		CVB_LAUNCHED();
+		{
+			KernelScope ks_("fast_emit_points", stream);
+			fast_emit_points_kernel<<<dim3(32, static_cast<unsigned>(batch)), 256, 0, stream>>>(p.list, p.listCount, p.listCap, p.mask,
+				d->prefix.as<unsigned int>(), words, p.W, threshold - 1, points, static_cast<unsigned int>(capacity), counts);
+		}
+		CVB_LAUNCHED();
+	}
+	return CVB200_S_OK;
+}
+
+extern "C" {
+
+int cvb200_corner_dete_new(cvb200_corner_dete_t** dete, int id)
+{
+	CVB_REQUIRE(dete, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(id == CVB200_FAST_ID, CVB200_E_INVALID_PARAMETER);
+	cvb200_corner_dete* d = new (std::nothrow) cvb200_corner_dete();
+	CVB_REQUIRE(d, CVB200_E_OUT_OF_MEMORY);
+	d->id = id; d->threshold = 20; d->type = CVB200_FAST_TYPE_9; d->N = 9; d->maxFeatures = 2000; d->nms = true; // fast_dete.cxx:74-80,111-125
+	*dete = d;
+	return CVB200_S_OK;
+}
+
+int cvb200_corner_dete_free(cvb200_corner_dete_t** dete)
+{
+	if (dete && *dete) {
+		cvb200_corner_dete* d = *dete;
+		d->mask.release(); d->prefix.release(); d->list.release(); d->counters.release(); d->hostIn.release(); d->points.release(); d->hostCount.release();
+		delete d;
+		*dete = nullptr;
+	}
+	return CVB200_S_OK;
+}
+
+// fast_dete.cxx:128-160
+int cvb200_corner_dete_set(cvb200_corner_dete_t* d, int id, const void* valuePtr, size_t valueSize)
+{
+	CVB_REQUIRE(d && valuePtr && valueSize, CVB200_E_INVALID_PARAMETER);
+	switch (id) {
+	case CVB200_FAST_SET_INT_THRESHOLD: {
+		CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
+		const int t = *static_cast<const int*>(valuePtr);
+		d->threshold = t < 0 ? 0 : (t > 255 ? 255 : t);
+		return CVB200_S_OK;
+	}
+	case CVB200_FAST_SET_INT_MAX_FEATURES:
+		CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
+		d->maxFeatures = *static_cast<const int*>(valuePtr);
+		return CVB200_S_OK;
+	case CVB200_FAST_SET_INT_FAST_TYPE: {
+		CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
+		const int t = *static_cast<const int*>(valuePtr);
+		CVB_REQUIRE(t == CVB200_FAST_TYPE_9 || t == CVB200_FAST_TYPE_12, CVB200_E_INVALID_PARAMETER);
+		d->type = t; d->N = (t == CVB200_FAST_TYPE_12) ? 12 : 9;
+		return CVB200_S_OK;
+	}
+	case CVB200_FAST_SET_BOOL_NON_MAXIMA_SUPP:
+		CVB_REQUIRE(valueSize == sizeof(bool), CVB200_E_INVALID_PARAMETER);
+		d->nms = *static_cast<const bool*>(valuePtr);
+		return CVB200_S_OK;
+	default:
+		return CVB200_E_NOT_IMPLEMENTED;
+	}
+}
+
+int cvb200_corner_dete_process_dev(cvb200_corner_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride,
+	cvb200_interest_point_t* points, size_t capacity, unsigned int* counts, size_t batch, size_t framePitch, cvb200_stream_t stream)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(d && image && points && counts && capacity && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(capacity < (1ull << 32), CVB200_E_OUT_OF_BOUND);
+	if (!batch) return CVB200_S_OK;
+	if (!framePitch) framePitch = stride * height;
+	std::lock_guard<std::mutex> lock(d->mutex);
+	return fast_launch(d, image, width, height, stride, batch, framePitch, nullptr, points, capacity, counts, d->threshold, d->N, d->nms, as_stream(stream));
+}
+
+int cvb200_corner_dete_process(cvb200_corner_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride,
+	cvb200_interest_point_t* points, size_t capacity, size_t* count)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(d && image && count && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(!capacity || points, CVB200_E_INVALID_PARAMETER);
+	*count = 0;
+	CVB_REQUIRE(width >= 4 && height >= 4, CVB200_E_INVALID_PARAMETER);
+	std::lock_guard<std::mutex> lock(d->mutex);
+	const size_t n = stride * height;
+	// device capacity: enough for every possible corner so that selectBest sees the full list like the reference does
+	size_t devCap = d->nms ? (width * height) / 4 + 16 : width * height;
+	CVB_CHECK(d->hostIn.ensure(n));
+	CVB_CHECK(d->points.ensure(devCap * sizeof(cvb200_interest_point_t) + sizeof(unsigned int)));
+	CVB_CHECK(d->hostCount.ensure(sizeof(unsigned int)));
+	cvb200_interest_point_t* dPts = d->points.as<cvb200_interest_point_t>();
+	unsigned int* dCount = reinterpret_cast<unsigned int*>(dPts + devCap);
+	CVB_CUDA(cudaMemcpyAsync(d->hostIn.p, image, n, cudaMemcpyHostToDevice, 0));
+	CVB_CHECK(fast_launch(d, d->hostIn.as<uint8_t>(), width, height, stride, 1, n, nullptr, dPts, devCap, dCount, d->threshold, d->N, d->nms, 0));
+	unsigned int* hCount = d->hostCount.as<unsigned int>();
+	CVB_CUDA(cudaMemcpyAsync(hCount, dCount, sizeof(unsigned int), cudaMemcpyDeviceToHost, 0));
+	CVB_CUDA(cudaStreamSynchronize(0));
+	size_t found = *hCount;
+	CVB_REQUIRE(found <= devCap, CVB200_E_OUT_OF_BOUND);
+	if (d->maxFeatures > 1 && found > static_cast<size_t>(d->maxFeatures)) {
+		// CompVInterestPoint::selectBest (compv_common.h:641-655): the same libstdc++ nth_element + partition on the same raster-ordered list,
+		// so ties at the cut resolve exactly as in the reference built with this toolchain
+		std::vector<cvb200_interest_point_t> v(found);
+		CVB_CUDA(cudaMemcpy(v.data(), dPts, found * sizeof(cvb200_interest_point_t), cudaMemcpyDeviceToHost));
+		const size_t max = static_cast<size_t>(d->maxFeatures);
+		std::nth_element(v.begin(), v.begin() + max, v.end(), [](const cvb200_interest_point_t& i, const cvb200_interest_point_t& j) { return i.strength > j.strength; });
+		const float pivot = v.at(max - 1).strength;
+		v.resize(std::partition(v.begin() + max, v.end(), [pivot](cvb200_interest_point_t i) { return i.strength >= pivot; }) - v.begin());
+		*count = v.size();
+		if (capacity) memcpy(points, v.data(), std::min(capacity, v.size()) * sizeof(cvb200_interest_point_t));
+		return v.size() > capacity && capacity ? CVB200_E_OUT_OF_BOUND : CVB200_S_OK;
+	}
+	*count = found;
+	if (capacity && found) CVB_CUDA(cudaMemcpy(points, dPts, std::min(capacity, found) * sizeof(cvb200_interest_point_t), cudaMemcpyDeviceToHost));
+	return (capacity && found > capacity) ? CVB200_E_OUT_OF_BOUND : CVB200_S_OK;
+}
+
+// K11 strength map == CompVGpuCornerDeteFAST::processData(IP, width, height, stride, N, threshold, strengths)
+int cvb200_fast_scores_dev(const uint8_t* image, size_t width, size_t height, size_t stride, int N, int threshold, uint8_t* strengths, size_t batch, size_t framePitch, cvb200_stream_t stream)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(image && strengths && image != strengths && width && height && stride >= width && (N == 9 || N == 12) && threshold >= 0 && threshold <= 255, CVB200_E_INVALID_PARAMETER);
+	if (!batch) return CVB200_S_OK;
+	if (!framePitch) framePitch = stride * height;
+	return fast_launch(nullptr, image, width, height, stride, batch, framePitch, strengths, nullptr, 0, nullptr, threshold, N, false, as_stream(stream));
+}
+
+int cvb200_fast_scores(const uint8_t* image, size_t width, size_t height, size_t stride, int N, int threshold, uint8_t* strengths)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(image && strengths && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
+	const size_t n = stride * height;
+	DevBuf dIn, dOut;
+	int rc = dIn.ensure(n);
+	if (!rc) rc = dOut.ensure(n);
+	if (!rc) rc = cvb200_memcpy_h2d(dIn.p, image, n, nullptr);
+	if (!rc) rc = cvb200_memset(dOut.p, 0, n, nullptr);
+	if (!rc) rc = cvb200_fast_scores_dev(dIn.as<uint8_t>(), width, height, stride, N, threshold, dOut.as<uint8_t>(), 1, 0, nullptr);
+	if (!rc) rc = cvb200_memcpy_d2h(strengths, dOut.p, n, nullptr);
+	if (!rc) rc = cvb200_stream_sync(nullptr);
+	dIn.release(); dOut.release();
+	return rc;
+}
+
+} // extern "C"

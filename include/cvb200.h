@@ -188,6 +188,34 @@ CVB200_API int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* dete, const uint
 CVB200_API int cvb200_sobel_g(const uint8_t* image, size_t width, size_t height, size_t stride, int id, size_t kernSize, int16_t* gx, int16_t* gy, uint16_t* g);
 CVB200_API int cvb200_sobel_g_dev(const uint8_t* image, size_t width, size_t height, size_t stride, int id, size_t kernSize, int16_t* gx, int16_t* gy, uint16_t* g, size_t batch, size_t framePitch, cvb200_stream_t stream);
 
+/* ================================================================================================
+ * a8 -- FAST9/FAST12 corners. Replaces CompVCornerDete::newObj(&f, COMPV_FAST_ID) + f->process(image, points)
+ * (core/features/fast/compv_core_feature_fast_dete.cxx:163-422; leaves :658-831, point list :490-585).
+ * ============================================================================================== */
+/* Binary layout of CompVInterestPoint (base/include/compv/base/compv_common.h:629-656): the adapter can memcpy into the std::vector */
+typedef struct cvb200_interest_point {
+	float x, y, strength, orient;
+	int32_t level;
+	float size;
+} cvb200_interest_point_t;
+typedef struct cvb200_corner_dete cvb200_corner_dete_t;
+CVB200_API int cvb200_corner_dete_new(cvb200_corner_dete_t** dete, int id /* CVB200_FAST_ID */);
+CVB200_API int cvb200_corner_dete_free(cvb200_corner_dete_t** dete);
+/* fast_dete.cxx:128-160: FAST_SET_INT_THRESHOLD (int, clipped 0..255), FAST_SET_INT_MAX_FEATURES (int), FAST_SET_INT_FAST_TYPE (int: FAST_TYPE_9/12),
+ * FAST_SET_BOOL_NON_MAXIMA_SUPP (bool). Defaults: threshold 20, FAST9, NMS on, maxFeatures 2000 (fast_dete.cxx:74-80). */
+CVB200_API int cvb200_corner_dete_set(cvb200_corner_dete_t* dete, int id, const void* valuePtr, size_t valueSize);
+/* Host frame in, points out in raster order (x, y, strength + threshold - 1). *count receives the number of points found (after selectBest when
+ * maxFeatures > 1 applies, compv_common.h:641-655); if it exceeds `capacity` the first `capacity` points are written and E_OUT_OF_BOUND is returned.
+ * capacity == 0 (points may be NULL) only counts. */
+CVB200_API int cvb200_corner_dete_process(cvb200_corner_dete_t* dete, const uint8_t* image, size_t width, size_t height, size_t stride, cvb200_interest_point_t* points, size_t capacity, size_t* count);
+/* Device frames in; points[frame*capacity + k] (device) in raster order, counts[frame] (device) = points found (may exceed capacity: excess dropped).
+ * maxFeatures/selectBest is NOT applied here (it is a host-side std::nth_element in the reference). Asynchronous. */
+CVB200_API int cvb200_corner_dete_process_dev(cvb200_corner_dete_t* dete, const uint8_t* image, size_t width, size_t height, size_t stride, cvb200_interest_point_t* points, size_t capacity, unsigned int* counts, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* K11 strength map, the shape of the reference's dormant hook CompVGpuCornerDeteFAST::processData(IP, width, height, stride, N, threshold, strengths)
+ * (gpu/include/compv/gpu/core/features/fast/compv_gpu_feature_fast_dete.h:23-47): strengths[y*stride+x] (before NMS), 0 on the 3-pixel border. N = 9 or 12. */
+CVB200_API int cvb200_fast_scores(const uint8_t* image, size_t width, size_t height, size_t stride, int N, int threshold, uint8_t* strengths);
+CVB200_API int cvb200_fast_scores_dev(const uint8_t* image, size_t width, size_t height, size_t stride, int N, int threshold, uint8_t* strengths, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,3 +212,31 @@ class RefEdgeSession:
             self.close()
         except Exception:
             pass
+
+
+POINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("strength", np.float32), ("orient", np.float32), ("level", np.int32), ("size", np.float32)])
+
+
+def fast_scores(img, N=9, threshold=20, width=None):
+    """Oracle strength map (K11), (h, stride) uint8."""
+    w, h, stride = _frame_args(img, width)
+    out = np.zeros((h, stride), np.uint8)
+    _chk(orc().orc_fast_scores(_p(img), _sz(w), _sz(h), _sz(stride), int(N), int(threshold), _p(out)), "orc_fast_scores")
+    return out
+
+
+def fast_detect(which, img, N=9, threshold=20, nms=True, max_features=-1, width=None, threads=1, iters=0):
+    """Interest points (structured array, POINT_DTYPE) in the order the implementation produced them.  With which='ref' and iters>0 also returns ms/iter."""
+    w, h, stride = _frame_args(img, width)
+    cap = w * h
+    pts = np.zeros(cap, POINT_DTYPE)
+    cnt = C.c_size_t(0)
+    if which == "orc":
+        assert max_features <= 1
+        _chk(orc().orc_fast_detect(_p(img), _sz(w), _sz(h), _sz(stride), int(N), int(threshold), int(bool(nms)), _p(pts), _sz(cap), C.byref(cnt)), "orc_fast_detect")
+        return pts[:cnt.value].copy()
+    ms = np.zeros(max(iters, 1), np.float64)
+    _chk(ref(threads).ref_fast_detect(_p(img), _sz(w), _sz(h), _sz(stride), int(N), int(threshold), int(bool(nms)), int(max_features), _p(pts), _sz(cap), C.byref(cnt),
+                                      int(iters), _p(ms)), "ref_fast_detect")
+    out = pts[:cnt.value].copy()
+    return (out, ms[:iters]) if iters else out

@@ -209,6 +209,34 @@ int ref_time_edge_dete(int which, const uint8_t* img, size_t w, size_t h, size_t
 	return 0;
 }
 
+// ---- a8: CompVCornerDete (FAST) through the factory (base/compv_features.cxx:80-95; core/features/fast/compv_core_feature_fast_dete.cxx:163-422) ----
+// fastType: 9 or 12. maxFeatures <= 1 disables selectBest. Points are copied out in the order the reference produced them.
+// pts layout == CompVInterestPoint (x, y, strength, orient, level, size). iters > 0: timed loop, ms per iteration written to msOut (may be NULL).
+int ref_fast_detect(const uint8_t* img, size_t w, size_t h, size_t stride, int fastType, int threshold, int nms, int maxFeatures,
+	void* pts, size_t capacity, size_t* count, int iters, double* msOut)
+{
+	CompVMatPtr image;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVCornerDetePtr dete;
+	SHIM_CHECK(CompVCornerDete::newObj(&dete, COMPV_FAST_ID));
+	SHIM_CHECK(dete->setInt(COMPV_FAST_SET_INT_THRESHOLD, threshold));
+	SHIM_CHECK(dete->setInt(COMPV_FAST_SET_INT_FAST_TYPE, fastType == 12 ? COMPV_FAST_TYPE_12 : COMPV_FAST_TYPE_9));
+	SHIM_CHECK(dete->setBool(COMPV_FAST_SET_BOOL_NON_MAXIMA_SUPP, nms != 0));
+	SHIM_CHECK(dete->setInt(COMPV_FAST_SET_INT_MAX_FEATURES, maxFeatures));
+	CompVInterestPointVector points;
+	SHIM_CHECK(dete->process(image, points));
+	for (int it = 0; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(dete->process(image, points));
+		if (msOut) msOut[it] = now_ms() - t0;
+	}
+	*count = points.size();
+	static_assert(sizeof(CompVInterestPoint) == 24, "CompVInterestPoint layout");
+	if (pts && capacity) memcpy(pts, points.data(), (points.size() < capacity ? points.size() : capacity) * sizeof(CompVInterestPoint));
+	return 0;
+}
+
 // Persistent edge-detection session for bench.py's CPU legs: frames are wrapped once (CompVImage::wrap), the detector, the Gaussian kernel and the
 // output matrices are created once, then ref_edge_session_run() times CompVMathConvlt::convlt1<u8,f32,u8> (optional) + CompVEdgeDete::process per frame.
 struct RefEdgeSession {
