@@ -240,3 +240,27 @@ def fast_detect(which, img, N=9, threshold=20, nms=True, max_features=-1, width=
                                       int(iters), _p(ms)), "ref_fast_detect")
     out = pts[:cnt.value].copy()
     return (out, ms[:iters]) if iters else out
+
+
+LINE_DTYPE = np.dtype([("rho", np.float32), ("theta", np.float32), ("strength", np.uint64)])
+
+
+def hough_kht(which, edges, rho=1.0, theta=1.0, threshold=1, max_lines=0, cluster_min_deviation=2.0, cluster_min_size=10, kernel_min_height=0.002,
+              width=None, threads=1, x86_simd=True, iters=0):
+    """KHT lines (structured array LINE_DTYPE, in detection order) and Gs.  which: 'orc' | 'ref'."""
+    w, h, stride = _frame_args(edges, width)
+    cap = 1 << 16
+    lines = np.zeros(cap, LINE_DTYPE)
+    cnt = C.c_size_t(0)
+    gs = C.c_double(0)
+    if which == "orc":
+        _chk(orc().orc_hough_kht(_p(edges), _sz(w), _sz(h), _sz(stride), C.c_float(rho), C.c_float(theta), _sz(threshold), C.c_float(cluster_min_deviation),
+                                 int(cluster_min_size), C.c_float(kernel_min_height), int(max_lines), int(bool(x86_simd)), _p(lines), _sz(cap), C.byref(cnt), C.byref(gs)),
+             "orc_hough_kht")
+        return lines[:min(cnt.value, cap)].copy(), gs.value
+    ms = np.zeros(max(iters, 1), np.float64)
+    _chk(ref(threads).ref_hough(1, _p(edges), _sz(w), _sz(h), _sz(stride), C.c_float(rho), C.c_float(theta), _sz(threshold), int(max_lines),
+                                C.c_float(cluster_min_deviation), int(cluster_min_size), C.c_float(kernel_min_height), _p(lines), _sz(cap), C.byref(cnt), C.byref(gs),
+                                int(iters), _p(ms)), "ref_hough")
+    out = lines[:min(cnt.value, cap)].copy()
+    return (out, gs.value, ms[:iters]) if iters else (out, gs.value)

@@ -237,6 +237,42 @@ int ref_fast_detect(const uint8_t* img, size_t w, size_t h, size_t stride, int f
 	return 0;
 }
 
+// ---- a6/a7: CompVHough (SHT / KHT) through the factory (base/compv_features.cxx:176-191) ----
+// which: 0 = COMPV_HOUGHSHT_ID, 1 = COMPV_HOUGHKHT_ID. theta is what CompVHough::newObj receives (KHT: degrees; SHT: see houghsht.cxx).
+// lines layout == CompVHoughLine {float rho; float theta; size_t strength}. iters > 0 adds a timed loop (ms per iteration in msOut, may be NULL).
+int ref_hough(int which, const uint8_t* edges, size_t w, size_t h, size_t stride, float rho, float theta, size_t threshold, int maxLines,
+	float khtClusterMinDeviation, int khtClusterMinSize, float khtKernelMinHeight,
+	void* lines, size_t capacity, size_t* count, double* gsOut, int iters, double* msOut)
+{
+	CompVMatPtr image;
+	int r = wrap8u(edges, w, h, stride, &image);
+	if (r) return r;
+	CompVHoughPtr hough;
+	SHIM_CHECK(CompVHough::newObj(&hough, which ? COMPV_HOUGHKHT_ID : COMPV_HOUGHSHT_ID, rho, theta, threshold));
+	if (maxLines > 0) SHIM_CHECK(hough->setInt(COMPV_HOUGH_SET_INT_MAXLINES, maxLines));
+	if (which) {
+		SHIM_CHECK(hough->setFloat32(COMPV_HOUGHKHT_SET_FLT32_CLUSTER_MIN_DEVIATION, khtClusterMinDeviation));
+		SHIM_CHECK(hough->setInt(COMPV_HOUGHKHT_SET_INT_CLUSTER_MIN_SIZE, khtClusterMinSize));
+		SHIM_CHECK(hough->setFloat32(COMPV_HOUGHKHT_SET_FLT32_KERNEL_MIN_HEIGTH, khtKernelMinHeight));
+	}
+	CompVHoughLineVector out;
+	SHIM_CHECK(hough->process(image, out));
+	for (int it = 0; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(hough->process(image, out));
+		if (msOut) msOut[it] = now_ms() - t0;
+	}
+	if (which && gsOut) {
+		compv_float64_t gs = 0;
+		SHIM_CHECK(hough->getFloat64(COMPV_HOUGHKHT_GET_FLT64_GS, &gs));
+		*gsOut = gs;
+	}
+	*count = out.size();
+	static_assert(sizeof(CompVHoughLine) == 16, "CompVHoughLine layout");
+	if (lines && capacity) memcpy(lines, out.data(), (out.size() < capacity ? out.size() : capacity) * sizeof(CompVHoughLine));
+	return 0;
+}
+
 // Persistent edge-detection session for bench.py's CPU legs: frames are wrapped once (CompVImage::wrap), the detector, the Gaussian kernel and the
 // output matrices are created once, then ref_edge_session_run() times CompVMathConvlt::convlt1<u8,f32,u8> (optional) + CompVEdgeDete::process per frame.
 struct RefEdgeSession {
