@@ -196,3 +196,62 @@ class CompVCornerDete:
                 lib().cvb200_corner_dete_free(C.byref(self._h))
         except Exception:
             pass
+
+
+# ---- a6 / a7: CompVHough ---------------------------------------------------------------------------
+LINE_DTYPE = np.dtype([("rho", np.float32), ("theta", np.float32), ("strength", np.uint64)])
+
+
+class CompVHough:
+    """Mirror of CompVHough (base/include/compv/base/compv_features.h:217-227) over cvb200_hough_*."""
+
+    HOUGH_SET_BOOL_X86_SIMD_SCAN = 1002
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def newObj(hough_id=HOUGHKHT_ID, rho=1.0, theta=1.0, threshold=1):
+        h = C.c_void_p()
+        check(lib().cvb200_hough_new(C.byref(h), int(hough_id), C.c_float(rho), C.c_float(theta), sz(threshold)), "cvb200_hough_new")
+        return CompVHough(h)
+
+    def set(self, cap_id, value, ctype):
+        v = ctype(value)
+        return lib().cvb200_hough_set(self._h, int(cap_id), C.byref(v), sz(C.sizeof(v)))
+
+    def setInt(self, cap_id, value):
+        check(self.set(cap_id, value, C.c_int32), "cvb200_hough_set")
+
+    def setFloat32(self, cap_id, value):
+        check(self.set(cap_id, value, C.c_float), "cvb200_hough_set")
+
+    def setBool(self, cap_id, value):
+        check(self.set(cap_id, bool(value), C.c_bool), "cvb200_hough_set")
+
+    def getFloat64(self, cap_id):
+        v = C.c_double(0)
+        check(lib().cvb200_hough_get(self._h, int(cap_id), C.byref(v), sz(8)), "cvb200_hough_get")
+        return v.value
+
+    def process(self, edges, width=None, capacity=1 << 16):
+        w, h, stride = _frame(edges, width)
+        lines = np.zeros(capacity, LINE_DTYPE)
+        cnt = C.c_size_t(0)
+        check(lib().cvb200_hough_process(self._h, vp(edges), sz(w), sz(h), sz(stride), vp(lines), sz(capacity), C.byref(cnt)), "cvb200_hough_process")
+        return lines[:min(cnt.value, capacity)].copy()
+
+    def process_dev(self, d_edges, width, height, stride, batch=1, frame_pitch=0, capacity=4096, stream=0):
+        """Device edge maps in; returns a list of per-frame line arrays (host)."""
+        lines = np.zeros((batch, capacity), LINE_DTYPE)
+        counts = np.zeros(batch, np.uint64)
+        check(lib().cvb200_hough_process_dev(self._h, vp(d_edges), sz(width), sz(height), sz(stride), sz(batch), sz(frame_pitch), vp(lines), sz(capacity), vp(counts),
+                                             C.c_void_p(stream)), "cvb200_hough_process_dev")
+        return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(batch)]
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cvb200_hough_free(C.byref(self._h))
+        except Exception:
+            pass

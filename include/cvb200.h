@@ -99,6 +99,10 @@ extern "C" {
 /* Extension, bool: force the generic (any kernel size / any stride) Canny front kernel instead of the TMA fast path. Test hook. */
 #define CVB200_EDGE_SET_BOOL_GENERIC_KERNEL             1001
 
+/* Extension, bool, Hough objects: reproduce what the reference's x86 SIMD build computes where it differs from its own scalar path (default true):
+ * kernel-height association of the SSE2/AVX leaves and the peak-scan coverage of the SSE2 leaf (see oracle/compv_oracle_kht.cpp header). */
+#define CVB200_HOUGH_SET_BOOL_X86_SIMD_SCAN             1002
+
 /* COMPV_BORDER_TYPE (compv_common.h) */
 #define CVB200_BORDER_TYPE_ZERO      0
 #define CVB200_BORDER_TYPE_IGNORE    1
@@ -215,6 +219,31 @@ CVB200_API int cvb200_corner_dete_process_dev(cvb200_corner_dete_t* dete, const 
  * (gpu/include/compv/gpu/core/features/fast/compv_gpu_feature_fast_dete.h:23-47): strengths[y*stride+x] (before NMS), 0 on the 3-pixel border. N = 9 or 12. */
 CVB200_API int cvb200_fast_scores(const uint8_t* image, size_t width, size_t height, size_t stride, int N, int threshold, uint8_t* strengths);
 CVB200_API int cvb200_fast_scores_dev(const uint8_t* image, size_t width, size_t height, size_t stride, int N, int threshold, uint8_t* strengths, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
+/* ================================================================================================
+ * a6/a7 -- Hough line detectors. Replaces CompVHough::newObj(&h, id, rho, theta, threshold) + h->process(edges, lines)
+ * (base/compv_features.cxx:176-191; KHT: core/features/hough/compv_core_feature_houghkht.cxx:208-447; SHT: compv_core_feature_houghsht.cxx:96-262).
+ * id in {CVB200_HOUGHKHT_ID, CVB200_HOUGHSHT_ID}. theta is the value the reference's newObj receives (KHT: degrees).
+ * ============================================================================================== */
+/* Binary layout of CompVHoughLine (base/include/compv/base/compv_common.h:686-692) */
+typedef struct cvb200_hough_line {
+	float rho;
+	float theta;
+	size_t strength;
+} cvb200_hough_line_t;
+typedef struct cvb200_hough cvb200_hough_t;
+CVB200_API int cvb200_hough_new(cvb200_hough_t** hough, int id, float rho, float theta, size_t threshold);
+CVB200_API int cvb200_hough_free(cvb200_hough_t** hough);
+/* houghkht.cxx:140-192: HOUGH_SET_FLT32_RHO / _THETA (float), HOUGH_SET_INT_THRESHOLD / _MAXLINES (int), HOUGHKHT_SET_FLT32_CLUSTER_MIN_DEVIATION (float),
+ * HOUGHKHT_SET_INT_CLUSTER_MIN_SIZE (int, >= 2 here), HOUGHKHT_SET_FLT32_KERNEL_MIN_HEIGTH (float), HOUGHKHT_SET_BOOL_OVERRIDE_INPUT_EDGES (bool, accepted, no effect) */
+CVB200_API int cvb200_hough_set(cvb200_hough_t* hough, int id, const void* valuePtr, size_t valueSize);
+/* houghkht.cxx:194-206: HOUGHKHT_GET_FLT64_GS -> double */
+CVB200_API int cvb200_hough_get(cvb200_hough_t* hough, int id, void* valuePtr, size_t valueSize);
+/* Host edge map (non-zero = edge) in; lines out, strongest first (the reference's order). *count = lines found (<= maxLines); at most `capacity` written. Synchronous. */
+CVB200_API int cvb200_hough_process(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t height, size_t stride, cvb200_hough_line_t* lines, size_t capacity, size_t* count);
+/* Device edge maps (batch) in; lines[frame*capacity + k] and counts[frame] are HOST arrays (the final peak ordering is the reference's std::sort + sweep,
+ * run on the host on a few thousand accumulator cells). Synchronous. */
+CVB200_API int cvb200_hough_process_dev(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cvb200_stream_t stream);
 
 #ifdef __cplusplus
 }

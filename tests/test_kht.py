@@ -62,3 +62,66 @@ def test_oracle_kht_empty_inputs():
         a, _ = oracle.hough_kht("orc", e)
         r, _ = oracle.hough_kht("ref", e, threads=1)
         same_lines(a, r)
+
+
+# ---------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(64, 48), (320, 200), (640, 480), (1920, 1080)])
+@pytest.mark.parametrize("threshold", [1, 100])
+def test_cuda_kht(cvb, w, h, threshold):
+    from compv_b200 import _ffi
+    d = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, threshold)
+    for e in edge_maps(w, h):
+        a = d.process(e)
+        o, gs = oracle.hough_kht("orc", e, 1.0, 1.0, threshold)
+        same_lines(a, o)
+        if len(o):
+            assert d.getFloat64(_ffi.HOUGHKHT_GET_FLT64_GS) == gs
+        if oracle.have_ref():
+            r, _ = oracle.hough_kht("ref", e, 1.0, 1.0, threshold, threads=1)
+            same_lines(a, r)
+
+
+@pytest.mark.gpu
+def test_cuda_kht_parameters_and_caps(cvb):
+    import ctypes
+    from compv_b200 import _ffi
+    e = canny_edges(frame_g(640, 480, 777))
+    for kw in [dict(rho=0.5, theta=0.5), dict(rho=1.0, theta=2.0, max_lines=5), dict(cluster_min_deviation=1.0, cluster_min_size=6), dict(kernel_min_height=0.05)]:
+        d = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, kw.get("rho", 1.0), kw.get("theta", 1.0), 10)
+        if "max_lines" in kw:
+            d.setInt(_ffi.HOUGH_SET_INT_MAXLINES, kw["max_lines"])
+        if "cluster_min_deviation" in kw:
+            d.setFloat32(_ffi.HOUGHKHT_SET_FLT32_CLUSTER_MIN_DEVIATION, kw["cluster_min_deviation"])
+            d.setInt(_ffi.HOUGHKHT_SET_INT_CLUSTER_MIN_SIZE, kw["cluster_min_size"])
+        if "kernel_min_height" in kw:
+            d.setFloat32(_ffi.HOUGHKHT_SET_FLT32_KERNEL_MIN_HEIGTH, kw["kernel_min_height"])
+        o, _ = oracle.hough_kht("orc", e, threshold=10, **kw)
+        same_lines(d.process(e), o)
+    d = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID)
+    assert d.set(_ffi.HOUGH_SET_FLT32_RHO, 2.0, ctypes.c_float) == _ffi.E_INVALID_PARAMETER      # houghkht.cxx:144
+    assert d.set(_ffi.HOUGH_SET_INT_THRESHOLD, 0, ctypes.c_int32) == _ffi.E_INVALID_PARAMETER    # houghkht.cxx:156
+    assert d.set(_ffi.HOUGH_SET_INT_MAXLINES, 1, ctypes.c_float) == _ffi.S_OK                    # only the size is checked (houghkht.cxx:162)
+    assert d.set(9999, 1, ctypes.c_int32) == _ffi.E_NOT_IMPLEMENTED
+    for e0 in [frame_const(64, 48, 0), frame_const(64, 48, 255)]:
+        same_lines(d.process(e0), oracle.hough_kht("orc", e0)[0])
+
+
+@pytest.mark.gpu
+def test_cuda_canny_then_kht_batched_on_device(cvb):
+    """The headline pipeline: fused Gaussian+Canny on the device, KHT on the device edge maps, whole batch per call."""
+    import torch
+    from compv_b200 import _ffi
+    w, h, batch = 1920, 1080, 3
+    frames = np.stack([frame_g(w, h, 12345 + k) for k in range(batch)])
+    d_in = torch.from_numpy(frames).cuda()
+    d_edges = torch.empty_like(d_in)
+    canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
+    canny.set_preblur(5, 1.0)
+    stream = torch.cuda.current_stream().cuda_stream
+    canny.process_dev(d_in, w, h, w, d_edges, batch=batch, stream=stream)
+    kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 100)
+    got = kht.process_dev(d_edges, w, h, w, batch=batch, stream=stream)
+    for k in range(batch):
+        want, _ = oracle.hough_kht("orc", canny_edges(frames[k]), 1.0, 1.0, 100)
+        same_lines(got[k], want)
