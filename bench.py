@@ -3,13 +3,14 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one pass of the hot path over one batch of synthetic 1920x1080 frames (BASELINE.json configs[1]):
-Gaussian 5x5 (sigma 1) -> Canny (Sobel 3x3, tLow 59, tHigh 119) per frame.  Frames are sharded across ranks with no
-data-path collective (weak scaling: every rank owns `--frames` frames).
+A "step" is one pass of the hot path over one batch of synthetic 1920x1080 frames (BASELINE.json configs[1] + configs[3], the
+configuration the metric "Canny+HoughKHT @1080p" is quoted on): Gaussian 5x5 (sigma 1) -> Canny (Sobel 3x3, tLow 59, tHigh 119)
+-> HoughKHT (rho 1, theta 1 degree, threshold 100) per frame.  Frames are sharded across ranks with no data-path collective
+(weak scaling: every rank owns `--frames` frames).
 
   value : whole-job Mpixels/s with the frames already resident in HBM (device API, CUDA events, max over ranks)
-  e2e   : the same metric through the reference-facing host call (cvb200_edge_dete_process_batch): pinned host frames in,
-          host edge maps out, H2D and D2H inside the timed region
+  e2e   : the same metric through the host call (cvb200_canny_kht_process_batch): pinned host frames in, lines out,
+          H2D and D2H inside the timed region
   roofline / cpu_baseline : see DESIGN.md section "Measurement"
 
 --impl reference times the UNMODIFIED reference (oracle/_ref, AVX2 intrinsics, all host threads) on the same config.
@@ -32,8 +33,11 @@ import numpy as np  # noqa: E402
 W, H = 1920, 1080
 TLOW, THIGH, KS = 59.0, 119.0, 3
 BLUR, SIGMA = 5, 1.0
-ALG_BYTES_PER_PX = 2.0  # 1 B/px read (frame) + 1 B/px written (edge map); blur and gradients stay on chip
-METRIC = "Mpixels/s Canny (Gaussian5x5+Sobel+NMS+hysteresis) @1080p"
+KHT_THRESHOLD = 100
+# Canny 1 B/px read (frame) + 1 B/px written (edge map), blur/gradients on chip; KHT 1 B/px read of the edge map
+ALG_BYTES_PER_PX = {"canny_front": 2.0, "kht_link": 1.0, "kht_bits": 1.0, "canny_hysteresis": 2.0, "canny_finalize": 2.0}
+METRIC = "Mpixels/s Canny+HoughKHT @1080p"
+WORKLOAD = "gauss5x5+canny+houghkht_1080p"
 
 
 def load_peaks():
@@ -95,7 +99,7 @@ def run_reference(args, rank, world):
     frames = make_frames(frames_per_step, 12345)
     r = oracle.ref(-1)
     threads = r.ref_threads_count()
-    sess = oracle.RefEdgeSession(frames, "canny", TLOW, THIGH, KS, BLUR, SIGMA, threads=-1)
+    sess = oracle.RefEdgeSession(frames, "canny", TLOW, THIGH, KS, BLUR, SIGMA, threads=-1, kht_threshold=KHT_THRESHOLD)
 
     def step():
         return sess.run(0, frames_per_step)[0]
@@ -111,8 +115,8 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16 (+f32 blur)",
-        "data": "synthetic", "config": {"workload": "gauss5x5+canny_1080p", "width": W, "height": H, "frames_per_step": frames_per_step,
-                                         "tLow": TLOW, "tHigh": THIGH, "kernSize": KS, "blur": [BLUR, SIGMA]},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "width": W, "height": H, "frames_per_step": frames_per_step,
+                                         "tLow": TLOW, "tHigh": THIGH, "kernSize": KS, "blur": [BLUR, SIGMA], "kht": {"rho": 1, "theta_deg": 1, "threshold": KHT_THRESHOLD}},
         "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": threads, "kind": "reference",
                          "sample": "%d frames/step x %d steps, CompV reference AVX2 intrinsics (asm disabled), %d pool threads on %d host cores" % (frames_per_step, args.steps, threads, cores)},
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -159,13 +163,16 @@ def main():
     d_out = torch.empty_like(d_in)
     dete = cvb.CompVEdgeDete.newObj(cvb.CANNY_ID, TLOW, THIGH, KS)
     dete.set_preblur(BLUR, SIGMA)
+    kht = cvb.CompVHough.newObj(cvb.HOUGHKHT_ID, 1.0, 1.0, KHT_THRESHOLD)
     stream = torch.cuda.current_stream().cuda_stream
+    nlines = [0]
 
     def step_dev():
         dete.process_dev(d_in, W, H, W, d_out, batch=B, stream=stream)
+        nlines[0] = sum(len(x) for x in kht.process_dev(d_out, W, H, W, batch=B, stream=stream))
 
     def step_e2e():
-        dete.process_batch(h_in.numpy(), width=W, edges=h_out.numpy())
+        nlines[0] = sum(len(x) for x in cvb.canny_kht_process_batch(dete, kht, h_in.numpy(), width=W))
 
     def barrier():
         if world > 1:
@@ -225,12 +232,15 @@ def main():
         for k in kernels.values():
             k["share"] = k["total_ms"] / psteps / step_ms
         peak, how = load_peaks()
-        alg_bytes = ALG_BYTES_PER_PX * B * W * H  # one launch of canny_front processes the whole batch
-        achieved = alg_bytes / (kernels[top]["avg_ms"] * 1e-3) / 1e9 if top == "canny_front" else \
-            alg_bytes / (kernels["canny_front"]["avg_ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "canny_front", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": how, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": kernels["canny_front"]["avg_ms"],
-                "top_kernel_by_time": top}
+        # the dominant kernel by device time; every launch of it processes the whole batch
+        alg_bytes = ALG_BYTES_PER_PX.get(top, 1.0) * B * W * H
+        achieved = alg_bytes / (kernels[top]["avg_ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": how, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": kernels[top]["avg_ms"],
+                "note": "kht_link is the order-dependent linking walk (one warp per frame): latency-bound by construction, see DESIGN.md" if top == "kht_link" else ""}
+        if "canny_front" in kernels and top != "canny_front":
+            cf = ALG_BYTES_PER_PX["canny_front"] * B * W * H / (kernels["canny_front"]["avg_ms"] * 1e-3) / 1e9
+            roof["canny_front"] = {"achieved": cf, "frac": cf / peak, "avg_launch_ms": kernels["canny_front"]["avg_ms"]}
 
     # ---- CPU baseline: the compiled reference on this host's cores (rank 0, N=1 only) ----
     cpu = None
@@ -239,11 +249,11 @@ def main():
             import oracle
             r = oracle.ref(-1)
             n = max(1, args.cpu_frames)
-            sess = oracle.RefEdgeSession(frames[:8], "canny", TLOW, THIGH, KS, BLUR, SIGMA, threads=-1)
+            sess = oracle.RefEdgeSession(frames[:8], "canny", TLOW, THIGH, KS, BLUR, SIGMA, threads=-1, kht_threshold=KHT_THRESHOLD)
             sess.run(0, 8)  # warm-up
             ms, _ = sess.run(0, n)
             cpu = {"value": n * W * H / 1e6 / (ms * 1e-3), "unit": "Mpixels/s", "cores": int(r.ref_threads_count()), "kind": "reference",
-                   "sample": "%d x 1080p frames (Gaussian5x5 + Canny, 8 distinct frames cycled), CompV reference, AVX2 intrinsics, asm disabled, %.3f ms/frame, %d host cores" % (n, ms / n, os.cpu_count())}
+                   "sample": "%d x 1080p frames (Gaussian5x5 + Canny + HoughKHT, 8 distinct frames cycled), CompV reference, AVX2 intrinsics, asm disabled, %.3f ms/frame, %d host cores" % (n, ms / n, os.cpu_count())}
         except Exception as ex:  # the bench line must still come out
             cpu = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (ex,)}
 
@@ -252,11 +262,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int16 (+f32 blur)", "data": "synthetic",
-            "config": {"workload": "gauss5x5+canny_1080p", "width": W, "height": H, "frames_per_gpu_per_step": B, "tLow": TLOW, "tHigh": THIGH,
-                       "kernSize": KS, "blur": [BLUR, SIGMA], "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6),
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "frames_per_gpu_per_step": B, "tLow": TLOW, "tHigh": THIGH,
+                       "kernSize": KS, "blur": [BLUR, SIGMA], "kht": {"rho": 1, "theta_deg": 1, "threshold": KHT_THRESHOLD}, "lines_per_step_rank0": nlines[0], "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6),
                        "parallelism": "frames sharded across %d GPU(s), no collective" % world},
-            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": B * W * H * world, "d2h_bytes_per_step": B * W * H * world,
-                    "ms_per_step": e2e_ms / args.steps, "api": "cvb200_edge_dete_process_batch (pinned host buffers)"},
+            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": B * W * H * world, "d2h_bytes_per_step": nlines[0] * 16 * world,
+                    "ms_per_step": e2e_ms / args.steps, "api": "cvb200_canny_kht_process_batch (pinned host frames in, lines out)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
         }
         print(json.dumps(line), flush=True)

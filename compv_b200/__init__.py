@@ -255,3 +255,15 @@ class CompVHough:
                 lib().cvb200_hough_free(C.byref(self._h))
         except Exception:
             pass
+
+
+def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
+    """Host frames (batch, height, stride) -> list of per-frame line arrays; cvb200_canny_kht_process_batch."""
+    assert images.ndim == 3 and images.flags.c_contiguous
+    b, h, stride = images.shape
+    w = stride if width is None else int(width)
+    lines = np.zeros((b, capacity), LINE_DTYPE)
+    counts = np.zeros(b, np.uint64)
+    check(lib().cvb200_canny_kht_process_batch(canny._h, hough._h, vp(images), sz(w), sz(h), sz(stride), sz(b), sz(h * stride), vp(lines), sz(capacity), vp(counts)),
+          "cvb200_canny_kht_process_batch")
+    return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]

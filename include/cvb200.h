@@ -245,6 +245,10 @@ CVB200_API int cvb200_hough_process(cvb200_hough_t* hough, const uint8_t* edges,
  * run on the host on a few thousand accumulator cells). Synchronous. */
 CVB200_API int cvb200_hough_process_dev(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cvb200_stream_t stream);
 
+/* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
+ * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
+CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,7 +179,7 @@ def time_edge_dete(img, kind="canny", tlow=59.0, thigh=119.0, ks=3, blur_size=0,
 class RefEdgeSession:
     """Reference detector + pre-wrapped frames created once; run() times blur (optional) + CompVEdgeDete::process over frames."""
 
-    def __init__(self, frames, kind="canny", tlow=59.0, thigh=119.0, ks=3, blur_size=0, blur_sigma=1.0, threads=-1, width=None):
+    def __init__(self, frames, kind="canny", tlow=59.0, thigh=119.0, ks=3, blur_size=0, blur_sigma=1.0, threads=-1, width=None, kht_threshold=0):
         assert frames.ndim == 3 and frames.flags.c_contiguous and frames.dtype == np.uint8
         n, h, stride = frames.shape
         w = stride if width is None else width
@@ -192,6 +192,8 @@ class RefEdgeSession:
                                                           int(ks), int(blur_size), C.c_float(blur_sigma)))
         if not self._s:
             raise RuntimeError("ref_edge_session_new failed")
+        if kht_threshold:
+            _chk(self._r.ref_edge_session_add_kht(self._s, _sz(kht_threshold)), "ref_edge_session_add_kht")
 
     def run(self, first=0, count=None, want_edges=False):
         """Returns (elapsed ms, last edge map or None)."""

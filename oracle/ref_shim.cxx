@@ -279,6 +279,9 @@ struct RefEdgeSession {
 	std::vector<CompVMatPtr> frames;
 	CompVMatPtr blurred, out, kernel;
 	CompVEdgeDetePtr dete;
+	CompVHoughPtr hough;        // optional: KHT on the edge map (BASELINE metric "Canny+HoughKHT")
+	CompVHoughLineVector lines;
+	size_t linesTotal;
 	int blurSize;
 };
 
@@ -287,6 +290,7 @@ void* ref_edge_session_new(int which, const uint8_t* frames, size_t count, size_
 	static const int ids[4] = { COMPV_SOBEL_ID, COMPV_SCHARR_ID, COMPV_PREWITT_ID, COMPV_CANNY_ID };
 	RefEdgeSession* s = new RefEdgeSession();
 	s->blurSize = blurSize;
+	s->linesTotal = 0;
 	for (size_t i = 0; i < count; ++i) {
 		CompVMatPtr m;
 		if (wrap8u(frames + i * stride * h, w, h, stride, &m)) { delete s; return NULL; }
@@ -299,6 +303,17 @@ void* ref_edge_session_new(int which, const uint8_t* frames, size_t count, size_
 	}
 	return s;
 }
+
+// Adds CompVHough (KHT, rho 1, theta 1 degree) after the edge detector of the session; returns 0 on success.
+int ref_edge_session_add_kht(void* session, size_t threshold)
+{
+	RefEdgeSession* s = static_cast<RefEdgeSession*>(session);
+	if (!s) return -1;
+	SHIM_CHECK(CompVHough::newObj(&s->hough, COMPV_HOUGHKHT_ID, 1.f, 1.f, threshold));
+	return 0;
+}
+
+size_t ref_edge_session_lines_total(void* session) { return session ? static_cast<RefEdgeSession*>(session)->linesTotal : 0; }
 
 // Processes frames[first .. first+count) (indices wrap around); returns elapsed milliseconds (steady_clock) or a negative error code.
 double ref_edge_session_run(void* session, size_t first, size_t count, uint8_t* lastEdges, size_t stride)
@@ -316,6 +331,10 @@ double ref_edge_session_run(void* session, size_t first, size_t count, uint8_t* 
 		}
 		else {
 			if (COMPV_ERROR_CODE_IS_NOK(s->dete->process(image, &s->out))) return -3.0;
+		}
+		if (s->hough) {
+			if (COMPV_ERROR_CODE_IS_NOK(s->hough->process(s->out, s->lines))) return -4.0;
+			s->linesTotal += s->lines.size();
 		}
 	}
 	const double t1 = now_ms();
