@@ -10,7 +10,7 @@ namespace {
 struct PipeState {
 	cudaStream_t sIn = nullptr, sCompute = nullptr;
 	cudaEvent_t evIn[2] = { nullptr, nullptr }, evDone[2] = { nullptr, nullptr };
-	DevBuf in[2], edges[2];
+	DevBuf in[2], edges; // input chunks are double buffered; the edge maps of the whole batch stay resident for one KHT call
 };
 thread_local PipeState t_pipe;
 }
@@ -33,13 +33,11 @@ extern "C" int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_
 		}
 	}
 	const size_t frameBytes = stride * height;
-	size_t chunk = (32u << 20) / frameBytes; // ~32 MiB per chunk: large enough to amortise the per-call synchronisations of the KHT host stage
+	size_t chunk = (16u << 20) / frameBytes; // ~16 MiB H2D chunks, overlapped with the Canny kernels of the previous chunk
 	if (chunk < 1) chunk = 1;
 	if (chunk > batch) chunk = batch;
-	for (int i = 0; i < 2; ++i) {
-		CVB_CHECK(st.in[i].ensure(chunk * frameBytes));
-		CVB_CHECK(st.edges[i].ensure(chunk * frameBytes));
-	}
+	for (int i = 0; i < 2; ++i) CVB_CHECK(st.in[i].ensure(chunk * frameBytes));
+	CVB_CHECK(st.edges.ensure(batch * frameBytes));
 	const size_t nChunks = div_up(batch, chunk);
 	auto h2d = [&](size_t c) -> int {
 		const int slot = static_cast<int>(c & 1);
@@ -55,12 +53,12 @@ extern "C" int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_
 		const size_t f0 = c * chunk, nf = (f0 + chunk <= batch) ? chunk : (batch - f0);
 		if (c + 1 < nChunks) CVB_CHECK(h2d(c + 1));
 		CVB_CUDA(cudaStreamWaitEvent(st.sCompute, st.evIn[slot], 0));
-		CVB_CHECK(cvb200_edge_dete_process_dev(canny, st.in[slot].as<uint8_t>(), width, height, stride, st.edges[slot].as<uint8_t>(), nf, frameBytes,
-			reinterpret_cast<cvb200_stream_t>(st.sCompute)));
-		CVB_CHECK(cvb200_hough_process_dev(hough, st.edges[slot].as<uint8_t>(), width, height, stride, nf, frameBytes, lines ? lines + f0 * capacity : nullptr, capacity, counts + f0,
+		CVB_CHECK(cvb200_edge_dete_process_dev(canny, st.in[slot].as<uint8_t>(), width, height, stride, st.edges.as<uint8_t>() + f0 * frameBytes, nf, frameBytes,
 			reinterpret_cast<cvb200_stream_t>(st.sCompute)));
 		CVB_CUDA(cudaEventRecord(st.evDone[slot], st.sCompute));
 	}
+	// the linking stage is latency bound with one warp per frame: its launch time does not depend on the number of frames, so the whole batch goes in one call
+	CVB_CHECK(cvb200_hough_process_dev(hough, st.edges.as<uint8_t>(), width, height, stride, batch, frameBytes, lines, capacity, counts, reinterpret_cast<cvb200_stream_t>(st.sCompute)));
 	CVB_CUDA(cudaStreamSynchronize(st.sCompute));
 	return CVB200_S_OK;
 }
