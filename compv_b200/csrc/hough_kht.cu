@@ -76,12 +76,9 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 }
 
 // ---- linking ------------------------------------------------------------------------------------
-// The walk reads a 3x3 neighbourhood and clears one bit per step: a chain of dependent accesses.  Straight from global memory every step pays an
-// L2 round trip (the store of the previous step invalidates the L1 line the next step needs): ~250 ns/px measured.  So the warp keeps a BAND of
-// KHT_BAND_ROWS full-width bitmap rows in shared memory, centred on the walk; steps are served from shared memory, erasures are written through to
-// global memory (the raster scan for the next seed reads global), and the band is re-centred cooperatively when the walk leaves it.
-constexpr int KHT_BAND_ROWS = 64;
-
+// Measured alternatives (bench_r1_c..f, frame G, 82k edge px, 5.9k walks per 1080p frame): this version 20.8 ms; shared-memory band caches of the
+// bitmap 30-47 ms.  The walk is a single dependent instruction chain on one lane, so its cost is (instructions per step) x (issue latency), not
+// memory: the variant with the fewest instructions wins.  Every access to a frame's bitmap comes from this one warp, so its SM's L1 stays coherent.
 // 3 neighbour bits (x-1, x, x+1) of a bitmap row -> bit0, bit1, bit2; out-of-image columns read as 0
 __device__ __forceinline__ unsigned int row3(const unsigned int* row, int x, int WW)
 {
@@ -93,10 +90,9 @@ __device__ __forceinline__ unsigned int row3(const unsigned int* row, int x, int
 }
 
 // Algorithm 6 (houghkht.cxx:666-703): first set neighbour in the order TL, T, TR, L, R, BL, B, BR. Rows outside the image do not exist.
-// `band` holds rows [bandY0, bandY0 + KHT_BAND_ROWS); the caller guarantees rows y-1..y+1 (those that exist) are inside it.
-__device__ __forceinline__ bool kht_next(const unsigned int* band, int bandY0, int& x, int& y, int H, int WW)
+__device__ __forceinline__ bool kht_next(const unsigned int* bits, int& x, int& y, int H, int WW)
 {
-	const unsigned int* rc = band + static_cast<size_t>(y - bandY0) * WW;
+	const unsigned int* rc = bits + static_cast<size_t>(y) * WW;
 	const unsigned int t = (y > 0) ? row3(rc - WW, x, WW) : 0u;
 	const unsigned int c = row3(rc, x, WW);
 	const unsigned int b = (y + 1 < H) ? row3(rc + WW, x, WW) : 0u;
@@ -107,15 +103,9 @@ __device__ __forceinline__ bool kht_next(const unsigned int* band, int bandY0, i
 	return false;
 }
 
-__device__ __forceinline__ bool kht_in_band(int y, int bandY0, int H)
-{
-	return (y == 0 || y - 1 >= bandY0) && (y == H - 1 || y + 1 < bandY0 + KHT_BAND_ROWS);
-}
-
 __global__ void __launch_bounds__(32)
 kht_link_kernel(unsigned int* __restrict__ bitsAll, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
 {
-	extern __shared__ unsigned int sBand[]; // KHT_BAND_ROWS x WW
 	const int frame = blockIdx.x, lane = threadIdx.x;
 	unsigned int* bits = bitsAll + static_cast<size_t>(frame) * g.H * g.WW;
 	KhtFrame& fr = frames[frame];
@@ -123,18 +113,6 @@ kht_link_kernel(unsigned int* __restrict__ bitsAll, ushort2* __restrict__ possAl
 	uint2* strings = stringsAll + fr.strOff;
 	unsigned int nPos = 0, nStr = 0; // meaningful on lane 0
 	const int W = g.W, H = g.H, WW = g.WW;
-	int bandY0 = -(1 << 20); // nothing cached yet
-
-	auto loadBand = [&](int yc) { // all lanes
-		int y0 = yc - KHT_BAND_ROWS / 2;
-		if (y0 > H - KHT_BAND_ROWS) y0 = H - KHT_BAND_ROWS;
-		if (y0 < 0) y0 = 0;
-		bandY0 = y0;
-		const int rows = min(KHT_BAND_ROWS, H - y0);
-		const unsigned int* src = bits + static_cast<size_t>(y0) * WW;
-		for (int i = lane; i < rows * WW; i += 32) sBand[i] = src[i];
-		__syncwarp();
-	};
 
 	for (int y = 1; y < H - 1; ++y) {
 		unsigned int* row = bits + static_cast<size_t>(y) * WW;
@@ -151,37 +129,23 @@ kht_link_kernel(unsigned int* __restrict__ bitsAll, ushort2* __restrict__ possAl
 				const int src = __ffs(any) - 1;
 				const unsigned int sw = __shfl_sync(0xffffffffu, w, src);
 				const int xr = (wb + src) * 32 + (__ffs(sw) - 1);
-				// Algorithm 5 (houghkht.cxx:706-760) as a resumable walk: lane 0 steps until the string ends or the walk leaves the band
-				unsigned int begin = nPos, rev = 0, end = 0;
-				int x = xr, yy = y;
-				int phase = 0;      // 0: first direction (push before stepping), 1: probe the second direction, 2: second direction, 3: done
-				if (!kht_in_band(yy, bandY0, H)) loadBand(yy);
-				while (true) {
-					int need = -1; // row the band must be re-centred on, or -1
-					if (lane == 0) {
-						while (phase != 3) {
-							if (!kht_in_band(yy, bandY0, H)) { need = yy; break; }
-							if (phase == 1) {
-								// one probe step from the reference pixel (already erased)
-								if (kht_next(sBand, bandY0, x, yy, H, WW)) phase = 2; else phase = 3;
-								continue;
-							}
-							// phases 0 and 2: record + erase the current pixel, then step
-							poss[nPos++] = make_ushort2(static_cast<unsigned short>(x), static_cast<unsigned short>(yy));
-							const unsigned int m = ~(1u << (x & 31));
-							sBand[static_cast<size_t>(yy - bandY0) * WW + (x >> 5)] &= m;
-							bits[static_cast<size_t>(yy) * WW + (x >> 5)] &= m; // write-through (the seed scan reads global memory)
-							if (!kht_next(sBand, bandY0, x, yy, H, WW)) {
-								if (phase == 0) { rev = nPos; x = xr; yy = y; phase = 1; }
-								else phase = 3;
-							}
-						}
-					}
-					need = __shfl_sync(0xffffffffu, need, 0);
-					if (need < 0) break;
-					loadBand(need);
-				}
+				unsigned int begin = 0, rev = 0, end = 0;
 				if (lane == 0) {
+					// Algorithm 5 (houghkht.cxx:706-760)
+					begin = nPos;
+					int x = xr, yy = y;
+					do {
+						poss[nPos++] = make_ushort2(static_cast<unsigned short>(x), static_cast<unsigned short>(yy));
+						bits[static_cast<size_t>(yy) * WW + (x >> 5)] &= ~(1u << (x & 31));
+					} while (kht_next(bits, x, yy, H, WW));
+					rev = nPos;
+					x = xr; yy = y;
+					if (kht_next(bits, x, yy, H, WW)) {
+						do {
+							poss[nPos++] = make_ushort2(static_cast<unsigned short>(x), static_cast<unsigned short>(yy));
+							bits[static_cast<size_t>(yy) * WW + (x >> 5)] &= ~(1u << (x & 31));
+						} while (kht_next(bits, x, yy, H, WW));
+					}
 					end = nPos;
 					if (end - begin < g.minSize) { nPos = begin; end = begin; }
 					else strings[nStr++] = make_uint2(begin, end);
@@ -686,10 +650,7 @@ static int kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, 
 	const unsigned int B = static_cast<unsigned int>(batch);
 
 	{ KernelScope ks_("kht_link", stream);
-	  const size_t bandBytes = static_cast<size_t>(KHT_BAND_ROWS) * g.WW * 4;
-	  CVB_REQUIRE(bandBytes <= 200 * 1024, CVB200_E_OUT_OF_BOUND);
-	  if (bandBytes > 48 * 1024) CVB_CUDA(cudaFuncSetAttribute(kht_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bandBytes)));
-	  kht_link_kernel<<<B, 32, bandBytes, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), dFrames, g); }
+	  kht_link_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), dFrames, g); }
 	CVB_LAUNCHED();
 	{ KernelScope ks_("kht_subdivide", stream);
 	  kht_subdivide_kernel<<<dim3(32, B), 64, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->clus.as<uint2>(), h->nClusStr.as<unsigned int>(), h->stack.as<KhtStack>(), dFrames, g); }
