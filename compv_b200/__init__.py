@@ -267,3 +267,36 @@ def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
     check(lib().cvb200_canny_kht_process_batch(canny._h, hough._h, vp(images), sz(w), sz(h), sz(stride), sz(b), sz(h * stride), vp(lines), sz(capacity), vp(counts)),
           "cvb200_canny_kht_process_batch")
     return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]
+
+
+# ---- a10: thresholding ------------------------------------------------------------------------------
+def histogram(img, width=None):
+    """CompVMathHistogram::build (8-bit): 256 uint32 bins."""
+    w, h, stride = _frame(img, width)
+    hist = np.zeros(256, np.uint32)
+    check(lib().cvb200_histogram_8u(vp(img), sz(w), sz(h), sz(stride), vp(hist)), "cvb200_histogram_8u")
+    return hist
+
+
+def threshold_global(img, threshold, width=None):
+    w, h, stride = _frame(img, width)
+    out = np.zeros((h, stride), np.uint8)
+    check(lib().cvb200_threshold_global(vp(img), sz(w), sz(h), sz(stride), C.c_double(threshold), vp(out)), "cvb200_threshold_global")
+    return out
+
+
+def threshold_otsu(img, width=None, want_output=True):
+    """Returns (out or None, threshold)."""
+    w, h, stride = _frame(img, width)
+    out = np.zeros((h, stride), np.uint8) if want_output else None
+    thr = C.c_double(0)
+    check(lib().cvb200_threshold_otsu(vp(img), sz(w), sz(h), sz(stride), C.byref(thr), vp(out)), "cvb200_threshold_otsu")
+    return out, thr.value
+
+
+def threshold_adaptive(img, block_size=5, delta=8.0, max_val=255.0, invert=False, width=None):
+    w, h, stride = _frame(img, width)
+    out = np.zeros((h, stride), np.uint8)
+    check(lib().cvb200_threshold_adaptive(vp(img), sz(w), sz(h), sz(stride), sz(block_size), C.c_double(delta), C.c_double(max_val), int(bool(invert)), vp(out)),
+          "cvb200_threshold_adaptive")
+    return out

@@ -245,6 +245,27 @@ CVB200_API int cvb200_hough_process(cvb200_hough_t* hough, const uint8_t* edges,
  * run on the host on a few thousand accumulator cells). Synchronous. */
 CVB200_API int cvb200_hough_process_dev(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cvb200_stream_t stream);
 
+/* ================================================================================================
+ * a10 -- thresholding. Replaces CompVImageThreshold::global / otsu / adaptive (base/image/compv_image_threshold.cxx:52-317, reached through
+ * CompVImage::thresholdGlobal / thresholdOtsu / thresholdAdaptive, base/include/compv/base/image/compv_image.h:63-67),
+ * CompVMathHistogram::build for 8-bit data (base/math/compv_math_histogram.cxx:44-61) and CompVKernel::mean (base/compv_kernel.cxx:12-25).
+ * ============================================================================================== */
+CVB200_API int cvb200_histogram_8u(const uint8_t* in, size_t width, size_t height, size_t stride, unsigned int* hist /* [256] */);
+CVB200_API int cvb200_histogram_8u_dev(const uint8_t* in, size_t width, size_t height, size_t stride, unsigned int* hist /* device [batch*256] */, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* out = in > uint8(clip(threshold)+0.5) ? 255 : 0. out may equal in. */
+CVB200_API int cvb200_threshold_global(const uint8_t* in, size_t width, size_t height, size_t stride, double threshold, uint8_t* out);
+CVB200_API int cvb200_threshold_global_dev(const uint8_t* in, size_t width, size_t height, size_t stride, double threshold, uint8_t* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* *threshold receives the Otsu threshold (an integer value, as a double like the reference); out may be NULL (threshold only). */
+CVB200_API int cvb200_threshold_otsu(const uint8_t* in, size_t width, size_t height, size_t stride, double* threshold, uint8_t* out);
+/* thresholds: device doubles [batch]; histScratch: device [batch*256] uint32 */
+CVB200_API int cvb200_threshold_otsu_dev(const uint8_t* in, size_t width, size_t height, size_t stride, double* thresholds, uint8_t* out, unsigned int* histScratch, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* mean kernel of `blockSize` (odd, <= 63) taps in fixed point, out = (in - mean > -delta) ? maxVal : 0 (inverted when invert != 0). out may equal in only for the host variant. */
+CVB200_API int cvb200_threshold_adaptive(const uint8_t* in, size_t width, size_t height, size_t stride, size_t blockSize, double delta, double maxVal, int invert, uint8_t* out);
+CVB200_API int cvb200_threshold_adaptive_dev(const uint8_t* in, size_t width, size_t height, size_t stride, size_t blockSize, double delta, double maxVal, int invert, uint8_t* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
+/* the overload taking separable fixed-point kernels (compv_image_threshold.cxx:200): kernels are HOST pointers */
+CVB200_API int cvb200_threshold_adaptive_kernel_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const uint16_t* kernelVt, const uint16_t* kernelHz, size_t kernSize, double delta, double maxVal, int invert, uint8_t* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_kernel_mean_fxp(size_t blockSize, uint16_t* kernel);
+
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
 CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);

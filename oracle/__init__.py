@@ -266,3 +266,30 @@ def hough_kht(which, edges, rho=1.0, theta=1.0, threshold=1, max_lines=0, cluste
                                 int(iters), _p(ms)), "ref_hough")
     out = lines[:min(cnt.value, cap)].copy()
     return (out, gs.value, ms[:iters]) if iters else (out, gs.value)
+
+
+def histogram(img, width=None):
+    w, h, stride = _frame_args(img, width)
+    hist = np.zeros(256, np.uint32)
+    _chk(orc().orc_histogram_8u(_p(img), _sz(w), _sz(h), _sz(stride), _p(hist)), "orc_histogram_8u")
+    return hist
+
+
+def threshold(which, mode, img, threshold=128.0, block_size=5, delta=8.0, max_val=255.0, invert=False, width=None, threads=1):
+    """mode: 'global' | 'otsu' | 'adaptive'.  Returns (out, otsu_threshold_or_None)."""
+    w, h, stride = _frame_args(img, width)
+    out = np.zeros((h, stride), np.uint8)
+    thr = C.c_double(0)
+    if which == "orc":
+        if mode == "global":
+            _chk(orc().orc_threshold_global(_p(img), _sz(w), _sz(h), _sz(stride), C.c_double(threshold), _p(out)), "orc_threshold_global")
+            return out, None
+        if mode == "otsu":
+            _chk(orc().orc_threshold_otsu(_p(img), _sz(w), _sz(h), _sz(stride), C.byref(thr), _p(out)), "orc_threshold_otsu")
+            return out, thr.value
+        _chk(orc().orc_threshold_adaptive(_p(img), _sz(w), _sz(h), _sz(stride), _sz(block_size), C.c_double(delta), C.c_double(max_val), int(bool(invert)), _p(out)), "orc_threshold_adaptive")
+        return out, None
+    m = {"global": 0, "otsu": 1, "adaptive": 2}[mode]
+    _chk(ref(threads).ref_threshold(m, _p(img), _sz(w), _sz(h), _sz(stride), C.c_double(threshold), _sz(block_size), C.c_double(delta), C.c_double(max_val), int(bool(invert)),
+                                    C.byref(thr), _p(out), 0, None), "ref_threshold")
+    return out, (thr.value if mode == "otsu" else None)

@@ -257,3 +257,76 @@ done:
     free(gx); free(gy); free(g); free(sup); free(stack);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * a10 thresholding.  base/image/compv_image_threshold.cxx
+ *   Otsu: histogram, sumA256[i] = i*h[i], fp32 between-class variance scan, strict '>' keeps the first maximum   :52-104, :349-366
+ *   global: out = in > uint8(clip(T)+0.5) ? 255 : 0                                                               :118-180, :319-347
+ *   adaptive: mean = fixed-point separable convolution with CompVKernel::mean taps (base/compv_kernel.cxx:12-25), out = lut[in - mean + 255]  :200-317
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API int orc_histogram_8u(const uint8_t* in, size_t w, size_t h, size_t stride, uint32_t* hist)
+{
+    if (!in || !hist || !w || !h || stride < w) return 20006;
+    memset(hist, 0, 256 * sizeof(uint32_t));
+    for (size_t y = 0; y < h; ++y) for (size_t x = 0; x < w; ++x) hist[in[y * stride + x]]++;
+    return 0;
+}
+
+ORC_API int orc_threshold_global(const uint8_t* in, size_t w, size_t h, size_t stride, double threshold, uint8_t* out)
+{
+    if (!in || !out || !w || !h || stride < w || threshold < 0) return 20006;
+    const double t = threshold > 255.0 ? 255.0 : threshold;
+    const uint8_t T = (uint8_t)(t + 0.5);
+    for (size_t y = 0; y < h; ++y) for (size_t x = 0; x < w; ++x) out[y * stride + x] = in[y * stride + x] > T ? 0xff : 0;
+    return 0;
+}
+
+ORC_API int orc_threshold_otsu(const uint8_t* in, size_t w, size_t h, size_t stride, double* threshold, uint8_t* out)
+{
+    uint32_t hist[256];
+    int rc = orc_histogram_8u(in, w, h, stride, hist);
+    if (rc) return rc;
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < 256; ++i) sum += i * hist[i];
+    const float sumf = (float)sum;
+    const int N = (int)(w * h);
+    volatile float sumB = 0.f, varMax = 0.f; /* volatile: every float operation rounds to fp32 individually */
+    int q1 = 0, thr = 0;
+    for (int i = 0; i < 256; ++i) {
+        q1 += (int)hist[i];
+        if (!q1) continue;
+        const int q2 = N - q1;
+        if (!q2) break;
+        const float q1f = (float)q1, q2f = (float)q2;
+        sumB += (float)(i * hist[i]);
+        volatile float a = sumB / q1f, b = (sumf - sumB), c = b / q2f;
+        volatile float mf = a - c;
+        volatile float v1 = q1f * q2f, v2 = v1 * mf, varB = v2 * mf;
+        if (varB > varMax) { varMax = varB; thr = i; }
+    }
+    *threshold = (double)thr;
+    return out ? orc_threshold_global(in, w, h, stride, *threshold, out) : 0;
+}
+
+ORC_API int orc_threshold_adaptive(const uint8_t* in, size_t w, size_t h, size_t stride, size_t blockSize, double delta, double maxVal, int invert, uint8_t* out)
+{
+    if (!in || !out || !(blockSize & 1) || maxVal < 0 || blockSize > 1024) return 20006;
+    uint16_t k[1024];
+    const float vvv = 1.f / (float)blockSize;
+    for (size_t i = 0; i < blockSize; ++i) k[i] = (uint16_t)(vvv * 0xffff);
+    uint8_t* mean = (uint8_t*)calloc(stride * h, 1);
+    if (!mean) return 20013;
+    int rc = orc_convlt1_fxp_8u16u8u(in, w, h, stride, k, k, blockSize, mean, 0);
+    if (!rc) {
+        const double dc = delta < 0.0 ? 0.0 : (delta > 255.0 ? 255.0 : delta), mc = maxVal > 255.0 ? 255.0 : maxVal;
+        const int deltaInt = (int)(dc + 0.5);
+        const uint8_t mv = (uint8_t)(mc + 0.5);
+        uint8_t lut[768];
+        const size_t offCount = (size_t)(255 - deltaInt + 1);
+        memset(lut, invert ? mv : 0, offCount);
+        memset(lut + offCount, invert ? 0 : mv, 768 - offCount);
+        for (size_t y = 0; y < h; ++y) for (size_t x = 0; x < w; ++x) out[y * stride + x] = lut[(int)in[y * stride + x] - (int)mean[y * stride + x] + 255];
+    }
+    free(mean);
+    return rc;
+}

@@ -273,6 +273,25 @@ int ref_hough(int which, const uint8_t* edges, size_t w, size_t h, size_t stride
 	return 0;
 }
 
+// ---- a10: CompVImage::thresholdOtsu / thresholdGlobal / thresholdAdaptive (base/include/compv/base/image/compv_image.h:63-67) ----
+// mode 0: global(threshold) ; 1: otsu (threshold written to *thrOut) ; 2: adaptive(blockSize, delta, maxVal, invert)
+int ref_threshold(int mode, const uint8_t* img, size_t w, size_t h, size_t stride, double threshold, size_t blockSize, double delta, double maxVal, int invert,
+	double* thrOut, uint8_t* outPtr, int iters, double* msOut)
+{
+	CompVMatPtr image, out;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	for (int it = -1; it < iters; ++it) {
+		const double t0 = now_ms();
+		if (mode == 0) SHIM_CHECK(CompVImage::thresholdGlobal(image, &out, threshold));
+		else if (mode == 1) { double t = 0; SHIM_CHECK(CompVImage::thresholdOtsu(image, t, &out)); if (thrOut) *thrOut = t; }
+		else SHIM_CHECK(CompVImage::thresholdAdaptive(image, &out, blockSize, delta, maxVal, invert != 0));
+		if (it >= 0 && msOut) msOut[it] = now_ms() - t0;
+	}
+	if (outPtr) copy_rows(out, outPtr, stride);
+	return 0;
+}
+
 // Persistent edge-detection session for bench.py's CPU legs: frames are wrapped once (CompVImage::wrap), the detector, the Gaussian kernel and the
 // output matrices are created once, then ref_edge_session_run() times CompVMathConvlt::convlt1<u8,f32,u8> (optional) + CompVEdgeDete::process per frame.
 struct RefEdgeSession {
