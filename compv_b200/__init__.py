@@ -300,3 +300,55 @@ def threshold_adaptive(img, block_size=5, delta=8.0, max_val=255.0, invert=False
     check(lib().cvb200_threshold_adaptive(vp(img), sz(w), sz(h), sz(stride), sz(block_size), C.c_double(delta), C.c_double(max_val), int(bool(invert)), vp(out)),
           "cvb200_threshold_adaptive")
     return out
+
+
+# ---- a4: CompVGradientFast, a9: CompVHOG ---------------------------------------------------------------
+def gradient_fast(img, width=None):
+    w, h, stride = _frame(img, width)
+    o = {"gx16": np.zeros((h, stride), np.int16), "gy16": np.zeros((h, stride), np.int16), "gx32": np.zeros((h, stride), np.float32),
+         "gy32": np.zeros((h, stride), np.float32), "mag": np.zeros((h, stride), np.float32), "dir": np.zeros((h, stride), np.float32)}
+    check(lib().cvb200_gradient_fast_8u(vp(img), sz(w), sz(h), sz(stride), vp(o["gx16"]), vp(o["gy16"]), vp(o["gx32"]), vp(o["gy32"]), vp(o["mag"]), vp(o["dir"])), "cvb200_gradient_fast_8u")
+    return o
+
+
+class CompVHOG:
+    """Mirror of CompVHOG (base/include/compv/base/compv_features.h:229-261) over cvb200_hog_*."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def newObj(hog_id=HOGS_ID, blockSize=(16, 16), blockStride=(8, 8), cellSize=(8, 8), nbins=9, blockNorm=_ffi.HOG_BLOCK_NORM_L2HYS, gradientSigned=True,
+               interp=_ffi.HOG_INTERPOLATION_BILINEAR):
+        h = C.c_void_p()
+        check(lib().cvb200_hog_new(C.byref(h), int(hog_id), sz(blockSize[0]), sz(blockSize[1]), sz(blockStride[0]), sz(blockStride[1]), sz(cellSize[0]), sz(cellSize[1]),
+                                   sz(nbins), int(blockNorm), int(bool(gradientSigned)), int(interp)), "cvb200_hog_new")
+        return CompVHOG(h)
+
+    def set(self, cap_id, value, ctype):
+        v = ctype(value)
+        return lib().cvb200_hog_set(self._h, int(cap_id), C.byref(v), sz(C.sizeof(v)))
+
+    def descriptorSize(self, width, height):
+        n = C.c_size_t(0)
+        check(lib().cvb200_hog_descriptor_size(self._h, sz(width), sz(height), C.byref(n)), "cvb200_hog_descriptor_size")
+        return n.value
+
+    def process(self, img, width=None):
+        w, h, stride = _frame(img, width)
+        n = self.descriptorSize(w, h)
+        out = np.zeros(n, np.float32)
+        size = C.c_size_t(0)
+        fn = lib().cvb200_hog_process if img.dtype == np.uint8 else lib().cvb200_hog_process_32f
+        check(fn(self._h, vp(img), sz(w), sz(h), sz(stride), vp(out), sz(n), C.byref(size)), "cvb200_hog_process")
+        return out[:size.value]
+
+    def process_dev(self, d_in, width, height, stride, d_out, batch=1, frame_pitch=0, stream=0):
+        check(lib().cvb200_hog_process_dev(self._h, vp(d_in), sz(width), sz(height), sz(stride), vp(d_out), sz(batch), sz(frame_pitch), C.c_void_p(stream)), "cvb200_hog_process_dev")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cvb200_hog_free(C.byref(self._h))
+        except Exception:
+            pass

@@ -266,6 +266,32 @@ CVB200_API int cvb200_threshold_adaptive_dev(const uint8_t* in, size_t width, si
 CVB200_API int cvb200_threshold_adaptive_kernel_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const uint16_t* kernelVt, const uint16_t* kernelHz, size_t kernSize, double delta, double maxVal, int invert, uint8_t* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
 CVB200_API int cvb200_kernel_mean_fxp(size_t blockSize, uint16_t* kernel);
 
+/* ================================================================================================
+ * a4 -- CompVGradientFast (base/compv_gradient_fast.cxx:58-433): gx = in[x+1]-in[x-1], gy = in[y+1]-in[y-1] (0 on the border), magnitude = sqrt(gx^2+gy^2)
+ * (CompVMathTrig::hypot_naive), direction = CompVMathTrig::fastAtan2 in DEGREES [0,360]. Every output pointer may be NULL.
+ * ============================================================================================== */
+CVB200_API int cvb200_gradient_fast_8u(const uint8_t* in, size_t width, size_t height, size_t stride, int16_t* gx16, int16_t* gy16, float* gx32, float* gy32, float* magnitude, float* direction);
+CVB200_API int cvb200_gradient_fast_8u_dev(const uint8_t* in, size_t width, size_t height, size_t stride, int16_t* gx16, int16_t* gy16, float* gx32, float* gy32, float* magnitude, float* direction, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_gradient_fast_32f_dev(const float* in, size_t width, size_t height, size_t stride, float* gx32, float* gy32, float* magnitude, float* direction, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
+/* ================================================================================================
+ * a9 -- S-HOG. Replaces CompVHOG::newObj(&hog, COMPV_HOGS_ID, blockSize, blockStride, cellSize, nbins, blockNorm, gradientSigned, interp) + hog->process(input, &output)
+ * (base/compv_features.cxx:210-299; core/features/hog/compv_core_feature_hog_std.cxx:196-393). The whole image is one window.
+ * ============================================================================================== */
+typedef struct cvb200_hog cvb200_hog_t;
+CVB200_API int cvb200_hog_new(cvb200_hog_t** hog, int id /* CVB200_HOGS_ID */, size_t blockW, size_t blockH, size_t strideW, size_t strideH, size_t cellW, size_t cellH, size_t nbins, int blockNorm, int gradientSigned, int interp);
+CVB200_API int cvb200_hog_free(cvb200_hog_t** hog);
+/* hog_std.cxx:124-178: HOG_SET_BOOL_GRADIENT_SIGNED (bool), HOG_SET_INT_BLOCK_NORM / _NBINS / _INTERPOLATION (int) */
+CVB200_API int cvb200_hog_set(cvb200_hog_t* hog, int id, const void* valuePtr, size_t valueSize);
+/* CompVHOG::descriptorSize (base/compv_features.cxx:274-299) */
+CVB200_API int cvb200_hog_descriptor_size(cvb200_hog_t* hog, size_t width, size_t height, size_t* size);
+/* *size = descriptor length; out (capacity floats) receives it (E_OUT_OF_BOUND when too small; out == NULL only queries the size) */
+CVB200_API int cvb200_hog_process(cvb200_hog_t* hog, const uint8_t* in, size_t width, size_t height, size_t stride, float* out, size_t capacity, size_t* size);
+CVB200_API int cvb200_hog_process_32f(cvb200_hog_t* hog, const float* in, size_t width, size_t height, size_t stride, float* out, size_t capacity, size_t* size);
+/* out: device, descriptor_size floats per frame, frames back to back */
+CVB200_API int cvb200_hog_process_dev(cvb200_hog_t* hog, const uint8_t* in, size_t width, size_t height, size_t stride, float* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
+CVB200_API int cvb200_hog_process_32f_dev(cvb200_hog_t* hog, const float* in, size_t width, size_t height, size_t stride, float* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
 CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);

@@ -293,3 +293,30 @@ def threshold(which, mode, img, threshold=128.0, block_size=5, delta=8.0, max_va
     _chk(ref(threads).ref_threshold(m, _p(img), _sz(w), _sz(h), _sz(stride), C.c_double(threshold), _sz(block_size), C.c_double(delta), C.c_double(max_val), int(bool(invert)),
                                     C.byref(thr), _p(out), 0, None), "ref_threshold")
     return out, (thr.value if mode == "otsu" else None)
+
+
+def gradient_fast(which, img, width=None):
+    """Returns dict gx16, gy16, gx32, gy32, mag, dir (degrees)."""
+    w, h, stride = _frame_args(img, width)
+    o = {"gx16": np.zeros((h, stride), np.int16), "gy16": np.zeros((h, stride), np.int16), "gx32": np.zeros((h, stride), np.float32),
+         "gy32": np.zeros((h, stride), np.float32), "mag": np.zeros((h, stride), np.float32), "dir": np.zeros((h, stride), np.float32)}
+    fn = orc().orc_gradient_fast_8u if which == "orc" else ref().ref_gradient_fast
+    _chk(fn(_p(img), _sz(w), _sz(h), _sz(stride), _p(o["gx16"]), _p(o["gy16"]), _p(o["gx32"]), _p(o["gy32"]), _p(o["mag"]), _p(o["dir"])), "gradient_fast")
+    return o
+
+
+def hog(which, img, block=(16, 16), stride_=(8, 8), cell=(8, 8), nbins=9, block_norm=52, gradient_signed=True, interp=55, width=None, threads=1, iters=0):
+    """S-HOG descriptor (float32 vector).  block_norm 48..52 (none, L1, L1sqrt, L2, L2Hys), interp 53..55 (nearest, bilinear LUT, bilinear)."""
+    w, h, stride = _frame_args(img, width)
+    size = C.c_size_t(0)
+    cap = 1 << 24
+    out = np.zeros(cap, np.float32)
+    if which == "orc":
+        _chk(orc().orc_hog(_p(img), _sz(w), _sz(h), _sz(stride), _sz(block[0]), _sz(block[1]), _sz(stride_[0]), _sz(stride_[1]), _sz(cell[0]), _sz(cell[1]), _sz(nbins),
+                           int(block_norm), int(bool(gradient_signed)), int(interp), _p(out), _sz(cap), C.byref(size)), "orc_hog")
+        return out[:size.value].copy()
+    ms = np.zeros(max(iters, 1), np.float64)
+    _chk(ref(threads).ref_hog(_p(img), _sz(w), _sz(h), _sz(stride), _sz(block[0]), _sz(block[1]), _sz(stride_[0]), _sz(stride_[1]), _sz(cell[0]), _sz(cell[1]), _sz(nbins),
+                              int(block_norm), int(bool(gradient_signed)), int(interp), _p(out), _sz(cap), C.byref(size), int(iters), _p(ms)), "ref_hog")
+    o = out[:size.value].copy()
+    return (o, ms[:iters]) if iters else o

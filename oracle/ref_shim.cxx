@@ -292,6 +292,46 @@ int ref_threshold(int mode, const uint8_t* img, size_t w, size_t h, size_t strid
 	return 0;
 }
 
+// ---- a4: CompVImage::gradientX/Y (base/image/compv_image.cxx:710-730) + CompVGradientFast::magnitude/direction ----
+int ref_gradient_fast(const uint8_t* img, size_t w, size_t h, size_t stride, int16_t* gx16, int16_t* gy16, float* gx32, float* gy32, float* mag, float* dir)
+{
+	CompVMatPtr image, a, b, c, d, m, dd;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	SHIM_CHECK(CompVImage::gradientX(image, &a, false));
+	SHIM_CHECK(CompVImage::gradientY(image, &b, false));
+	SHIM_CHECK(CompVImage::gradientX(image, &c, true));
+	SHIM_CHECK(CompVImage::gradientY(image, &d, true));
+	SHIM_CHECK(CompVGradientFast::magnitude(c, d, &m));
+	SHIM_CHECK(CompVGradientFast::direction(c, d, &dd, true));
+	if (gx16) copy_rows(a, gx16, stride * 2);
+	if (gy16) copy_rows(b, gy16, stride * 2);
+	if (gx32) copy_rows(c, gx32, stride * 4);
+	if (gy32) copy_rows(d, gy32, stride * 4);
+	if (mag) copy_rows(m, mag, stride * 4);
+	if (dir) copy_rows(dd, dir, stride * 4);
+	return 0;
+}
+
+// ---- a9: CompVHOG through the factory (base/compv_features.cxx:210-235; core/features/hog/compv_core_feature_hog_std.cxx:196-393) ----
+int ref_hog(const uint8_t* img, size_t w, size_t h, size_t stride, size_t bw, size_t bh, size_t sw, size_t sh, size_t cw, size_t ch, size_t nbins, int blockNorm, int gradientSigned, int interp,
+	float* out, size_t capacity, size_t* size, int iters, double* msOut)
+{
+	CompVMatPtr image, desc;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVHOGPtr hog;
+	SHIM_CHECK(CompVHOG::newObj(&hog, COMPV_HOGS_ID, CompVSizeSz(bw, bh), CompVSizeSz(sw, sh), CompVSizeSz(cw, ch), nbins, blockNorm, gradientSigned != 0, interp));
+	for (int it = -1; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(hog->process(image, &desc));
+		if (it >= 0 && msOut) msOut[it] = now_ms() - t0;
+	}
+	*size = desc->cols();
+	if (out) memcpy(out, desc->ptr<const float>(), (desc->cols() < capacity ? desc->cols() : capacity) * sizeof(float));
+	return 0;
+}
+
 // Persistent edge-detection session for bench.py's CPU legs: frames are wrapped once (CompVImage::wrap), the detector, the Gaussian kernel and the
 // output matrices are created once, then ref_edge_session_run() times CompVMathConvlt::convlt1<u8,f32,u8> (optional) + CompVEdgeDete::process per frame.
 struct RefEdgeSession {
