@@ -170,10 +170,10 @@ def main():
 
     def step_dev():
         dete.process_dev(d_in, W, H, W, d_out, batch=B, stream=stream)
-        nlines[0] = sum(len(x) for x in kht.process_dev(d_out, W, H, W, batch=B, stream=stream))
+        nlines[0] = sum(len(x) for x in kht.process_dev(d_out, W, H, W, batch=B, capacity=512, stream=stream))
 
     def step_e2e():
-        nlines[0] = sum(len(x) for x in cvb.canny_kht_process_batch(dete, kht, h_in.numpy(), width=W))
+        nlines[0] = sum(len(x) for x in cvb.canny_kht_process_batch(dete, kht, h_in.numpy(), width=W, capacity=512))
 
     def barrier():
         if world > 1:
