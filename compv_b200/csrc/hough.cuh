@@ -1,0 +1,26 @@
+// The object behind cvb200_hough_t: one struct for both line detectors (CompVHough::newObj picks the implementation by id, base/compv_features.cxx:176-191).
+#pragma once
+#include "common.cuh"
+
+struct cvb200_hough {
+	int id;
+	float rho, theta;           // as handed to newObj
+	size_t threshold;
+	int maxLines;
+	float clusterMinDeviation; int clusterMinSize; float kernelMinHeight;
+	bool x86Simd;
+	double lastGs;
+	// KHT scratch (hough_kht.cu)
+	cvb::DevBuf bits, poss, strings, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
+	cvb::HostBuf hFrames, hVotes, hCounts;
+	// SHT scratch (hough_sht.cu)
+	cvb::DevBuf shtTables, shtList, shtCursor, shtMask, shtPool, shtDesc;
+	std::mutex mutex;
+};
+
+namespace cvb {
+int kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
+	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream);
+int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
+	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream);
+}

@@ -15,7 +15,7 @@
 //   kht_subdivide one thread per string: the recursive segmentation as an explicit-stack post-order walk
 //   kht_scan / kht_kernels / kht_hmax / kht_gmin / kht_vote (one thread per kernel quadrant, integer atomicAdd) / kht_peaks (+ rank prefix)
 // Host: the thresholded, smoothed cells (a few thousand per frame) are sorted with the same libstdc++ std::sort as the reference and swept.
-#include "common.cuh"
+#include "hough.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -556,20 +556,8 @@ kht_peaks_emit_kernel(const int* __restrict__ accAll, const unsigned int* __rest
 
 using namespace cvb;
 
-struct cvb200_hough {
-	int id;
-	float rho, theta;           // as handed to newObj
-	size_t threshold;
-	int maxLines;
-	float clusterMinDeviation; int clusterMinSize; float kernelMinHeight;
-	bool x86Simd;
-	double lastGs;
-	DevBuf bits, poss, strings, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
-	HostBuf hFrames, hVotes, hCounts;
-	std::mutex mutex;
-};
 
-static int kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
+int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
 	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream)
 {
 	CVB_REQUIRE(width <= 65535 && height <= 65535, CVB200_E_OUT_OF_BOUND); // positions are stored as 16-bit coordinates
@@ -746,7 +734,8 @@ int cvb200_hough_new(cvb200_hough_t** hough, int id, float rho, float theta, siz
 	CVB_REQUIRE(hough, CVB200_E_INVALID_PARAMETER);
 	CVB_REQUIRE_INIT();
 	CVB_REQUIRE(id == CVB200_HOUGHKHT_ID || id == CVB200_HOUGHSHT_ID, CVB200_E_INVALID_PARAMETER);
-	CVB_REQUIRE(rho > 0.f && rho <= 1.f, CVB200_E_INVALID_PARAMETER); // houghkht.cxx:493
+	CVB_REQUIRE(rho > 0.f && rho <= 1.f, CVB200_E_INVALID_PARAMETER); // houghkht.cxx:493, houghsht.cxx:310
+	CVB_REQUIRE(id == CVB200_HOUGHKHT_ID || rho == 1.f, CVB200_E_INVALID_PARAMETER); // houghsht.cxx:312: the SHT requires rho == 1
 	cvb200_hough* h = new (std::nothrow) cvb200_hough();
 	CVB_REQUIRE(h, CVB200_E_OUT_OF_MEMORY);
 	h->id = id; h->rho = rho; h->theta = theta; h->threshold = threshold;
@@ -761,7 +750,8 @@ int cvb200_hough_free(cvb200_hough_t** hough)
 {
 	if (hough && *hough) {
 		cvb200_hough* h = *hough;
-		DevBuf* bufs[] = { &h->bits, &h->poss, &h->strings, &h->clus, &h->clusOrd, &h->nClusStr, &h->stack, &h->kern, &h->acc, &h->rowCount, &h->votes, &h->frames, &h->edgeCount, &h->hostIn };
+		DevBuf* bufs[] = { &h->bits, &h->poss, &h->strings, &h->clus, &h->clusOrd, &h->nClusStr, &h->stack, &h->kern, &h->acc, &h->rowCount, &h->votes, &h->frames, &h->edgeCount, &h->hostIn,
+			&h->shtTables, &h->shtList, &h->shtCursor, &h->shtMask, &h->shtPool, &h->shtDesc };
 		for (DevBuf* b : bufs) b->release();
 		h->hFrames.release(); h->hVotes.release(); h->hCounts.release();
 		delete h;
@@ -779,6 +769,7 @@ int cvb200_hough_set(cvb200_hough_t* h, int id, const void* valuePtr, size_t val
 		CVB_REQUIRE(valueSize == sizeof(float), CVB200_E_INVALID_PARAMETER);
 		const float v = *static_cast<const float*>(valuePtr);
 		CVB_REQUIRE(v > 0.f && v <= 1.f, CVB200_E_INVALID_PARAMETER);
+		CVB_REQUIRE(h->id == CVB200_HOUGHKHT_ID || v == 1.f, CVB200_E_INVALID_PARAMETER); // houghsht.cxx:71
 		h->rho = v; return CVB200_S_OK;
 	}
 	case CVB200_HOUGH_SET_FLT32_THETA: {
@@ -839,7 +830,7 @@ int cvb200_hough_process_dev(cvb200_hough_t* h, const uint8_t* edges, size_t wid
 	std::lock_guard<std::mutex> lock(h->mutex);
 	for (size_t f = 0; f < batch; ++f) counts[f] = 0;
 	if (h->id == CVB200_HOUGHKHT_ID) return kht_process_dev(h, edges, width, height, stride, batch, framePitch, lines, capacity, counts, as_stream(stream));
-	return CVB200_E_NOT_IMPLEMENTED;
+	return sht_process_dev(h, edges, width, height, stride, batch, framePitch, lines, capacity, counts, as_stream(stream));
 }
 
 int cvb200_hough_process(cvb200_hough_t* h, const uint8_t* edges, size_t width, size_t height, size_t stride, cvb200_hough_line_t* lines, size_t capacity, size_t* count)

@@ -268,6 +268,31 @@ def hough_kht(which, edges, rho=1.0, theta=1.0, threshold=1, max_lines=0, cluste
     return (out, gs.value, ms[:iters]) if iters else (out, gs.value)
 
 
+def hough_sht(which, edges, rho=1.0, theta=1.0, threshold=1, max_lines=0, width=None, threads=1, x86_simd=True, iters=0, cap=1 << 16):
+    """SHT lines (LINE_DTYPE, sorted by strength as the reference returns them) and the untruncated count.  which: 'orc' | 'ref'.
+    x86_simd=False selects the generic C++ path (for 'ref': SIMD disabled around the call)."""
+    w, h, stride = _frame_args(edges, width)
+    lines = np.zeros(cap, LINE_DTYPE)
+    cnt = C.c_size_t(0)
+    if which == "orc":
+        _chk(orc().orc_hough_sht(_p(edges), _sz(w), _sz(h), _sz(stride), C.c_float(rho), C.c_float(theta), _sz(threshold), int(max_lines), int(bool(x86_simd)),
+                                 _p(lines), _sz(cap), C.byref(cnt)), "orc_hough_sht")
+        return lines[:min(cnt.value, cap)].copy(), cnt.value
+    gs = C.c_double(0)
+    ms = np.zeros(max(iters, 1), np.float64)
+    r = ref(threads)
+    if not x86_simd:
+        _chk(r.ref_cpu_simd(0), "ref_cpu_simd")
+    try:
+        _chk(r.ref_hough(0, _p(edges), _sz(w), _sz(h), _sz(stride), C.c_float(rho), C.c_float(theta), _sz(threshold), int(max_lines),
+                         C.c_float(0), 0, C.c_float(0), _p(lines), _sz(cap), C.byref(cnt), C.byref(gs), int(iters), _p(ms)), "ref_hough")
+    finally:
+        if not x86_simd:
+            _chk(r.ref_cpu_simd(1), "ref_cpu_simd")
+    out = lines[:min(cnt.value, cap)].copy()
+    return (out, cnt.value, ms[:iters]) if iters else (out, cnt.value)
+
+
 def histogram(img, width=None):
     w, h, stride = _frame_args(img, width)
     hist = np.zeros(256, np.uint32)
