@@ -257,6 +257,91 @@ class CompVHough:
             pass
 
 
+RANGE_DTYPE = np.dtype([("a", np.int32), ("start", np.int16), ("end", np.int16)])
+
+
+class CompVConnectedComponentLabelingResult:
+    """Mirror of CompVConnectedComponentLabelingResultLSL (base/include/compv/base/compv_ccl.h:138-156) over cvb200_ccl_result_*."""
+
+    def __init__(self, handle, width, height):
+        self._h = handle
+        self.width, self.height = width, height
+
+    def labelsCount(self):
+        return int(lib().cvb200_ccl_result_labels_count(self._h))
+
+    def labelIds(self):
+        return np.arange(1, self.labelsCount() + 1, dtype=np.int32)
+
+    def segments(self):
+        """(row_offsets uint32 (height+1), ranges RANGE_DTYPE): the LEA in CSR form."""
+        ro, rg, n = C.POINTER(C.c_uint32)(), C.c_void_p(), C.c_size_t(0)
+        check(lib().cvb200_ccl_result_segments(self._h, C.byref(ro), C.byref(rg), C.byref(n)), "cvb200_ccl_result_segments")
+        row_offsets = np.ctypeslib.as_array(ro, shape=(self.height + 1,)).copy()
+        if not n.value:
+            return row_offsets, np.zeros(0, RANGE_DTYPE)
+        buf = (C.c_char * (n.value * RANGE_DTYPE.itemsize)).from_address(rg.value)
+        return row_offsets, np.frombuffer(buf, RANGE_DTYPE).copy()
+
+    def debugFlatten(self):
+        labels = np.zeros((self.height, self.width), np.int32)
+        check(lib().cvb200_ccl_result_flatten(self._h, vp(labels), sz(self.width)), "cvb200_ccl_result_flatten")
+        return labels
+
+    def boundingBoxes(self):
+        n = C.c_size_t(0)
+        boxes = np.zeros((max(1, self.labelsCount()), 4), np.int16)
+        check(lib().cvb200_ccl_result_bounding_boxes(self._h, vp(boxes), sz(len(boxes)), C.byref(n)), "cvb200_ccl_result_bounding_boxes")
+        return boxes[:n.value].copy()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cvb200_ccl_result_free(C.byref(self._h))
+        except Exception:
+            pass
+
+
+class CompVConnectedComponentLabeling:
+    """Mirror of CompVConnectedComponentLabeling (base/include/compv/base/compv_ccl.h:173-241) over cvb200_ccl_*."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def newObj(ccl_id=_ffi.PLSL_ID):
+        h = C.c_void_p()
+        check(lib().cvb200_ccl_new(C.byref(h), int(ccl_id)), "cvb200_ccl_new")
+        return CompVConnectedComponentLabeling(h)
+
+    def set(self, cap_id, value, ctype):
+        v = ctype(value)
+        return lib().cvb200_ccl_set(self._h, int(cap_id), C.byref(v), sz(C.sizeof(v)))
+
+    def process(self, binar, width=None):
+        w, h, stride = _frame(binar, width)
+        r = C.c_void_p()
+        check(lib().cvb200_ccl_process(self._h, vp(binar), sz(w), sz(h), sz(stride), C.byref(r)), "cvb200_ccl_process")
+        return CompVConnectedComponentLabelingResult(r, w, h)
+
+    def process_dev(self, d_binar, width, height, stride, batch=1, frame_pitch=0, d_labels=None, want_results=False, stream=0):
+        """Device frames in; returns (na int32 array, list of results or None).  d_labels (device int32, batch*height*width) receives the label images."""
+        na = np.zeros(batch, np.int32)
+        handles = (C.c_void_p * batch)()
+        check(lib().cvb200_ccl_process_dev(self._h, vp(d_binar), sz(width), sz(height), sz(stride), sz(batch), sz(frame_pitch),
+                                           vp(d_labels) if d_labels is not None else None, vp(na), handles if want_results else None, C.c_void_p(stream)),
+              "cvb200_ccl_process_dev")
+        results = [CompVConnectedComponentLabelingResult(C.c_void_p(handles[f]), width, height) for f in range(batch)] if want_results else None
+        return na, results
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cvb200_ccl_free(C.byref(self._h))
+        except Exception:
+            pass
+
+
 def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
     """Host frames (batch, height, stride) -> list of per-frame line arrays; cvb200_canny_kht_process_batch."""
     assert images.ndim == 3 and images.flags.c_contiguous

@@ -58,6 +58,11 @@ HOG_INTERPOLATION_NEAREST = 53
 HOG_INTERPOLATION_BILINEAR_LUT = 54
 HOG_INTERPOLATION_BILINEAR = 55
 PLSL_ID = 1
+CCL_SET_INT_CONNECTIVITY = 0
+PLSL_SET_INT_TYPE = 2
+PLSL_SET_BOOL_SORT_SEGMENTS = 3
+PLSL_TYPE_XRLEZ = 10
+PLSL_TYPE_STD = 4
 LMSER_ID = 19
 BORDER_TYPE_ZERO = 0
 BORDER_TYPE_IGNORE = 1
@@ -89,6 +94,7 @@ def lib():
         _lib.cvb200_error_string.restype = C.c_char_p
         _lib.cvb200_last_cuda_error.restype = C.c_char_p
         _lib.cvb200_launch_count.restype = C.c_uint64
+        _lib.cvb200_ccl_result_labels_count.restype = C.c_size_t
     return _lib
 
 

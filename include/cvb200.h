@@ -87,7 +87,11 @@ extern "C" {
 #define CVB200_HOG_INTERPOLATION_NEAREST                53
 #define CVB200_HOG_INTERPOLATION_BILINEAR_LUT           54
 #define CVB200_HOG_INTERPOLATION_BILINEAR               55
-#define CVB200_PLSL_ID                                  1   /* compv_ccl.h enum (separate id space) */
+#define CVB200_CCL_SET_INT_CONNECTIVITY                 0   /* compv_ccl.h:63-103 enum (separate id space) */
+#define CVB200_PLSL_ID                                  1
+#define CVB200_PLSL_SET_INT_TYPE                        2
+#define CVB200_PLSL_SET_BOOL_SORT_SEGMENTS              3
+#define CVB200_PLSL_TYPE_XRLEZ                          10
 #define CVB200_LMSER_ID                                 19
 
 /* Extension (not a reference id): Sobel/Scharr/Prewitt objects only, bool. When true, gmax is taken over the columns x with
@@ -291,6 +295,37 @@ CVB200_API int cvb200_hog_process_32f(cvb200_hog_t* hog, const float* in, size_t
 /* out: device, descriptor_size floats per frame, frames back to back */
 CVB200_API int cvb200_hog_process_dev(cvb200_hog_t* hog, const uint8_t* in, size_t width, size_t height, size_t stride, float* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
 CVB200_API int cvb200_hog_process_32f_dev(cvb200_hog_t* hog, const float* in, size_t width, size_t height, size_t stride, float* out, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
+/* ================================================================================================
+ * a11 -- connected component labeling, Parallel Light Speed Labeling. Replaces CompVConnectedComponentLabeling::newObj(&ccl, COMPV_PLSL_ID) + ccl->process(binar, &result)
+ * (base/compv_ccl.cxx:69-97; core/ccl/compv_core_ccl_lsl.cxx:579-751) and the result class CompVConnectedComponentLabelingResultLSLImpl
+ * (core/include/compv/core/ccl/compv_core_ccl_lsl_result.h:43-83, core/ccl/compv_core_ccl_lsl_result.cxx).
+ * The input must be binary (0x00 / 0x01 / 0xff, ccl_lsl.cxx:578: only bit 0 is looked at); 8-connectivity; labels 1..na exactly as the reference numbers them.
+ * width, height <= 32767 (the reference stores positions as int16).
+ * ============================================================================================== */
+typedef struct cvb200_ccl cvb200_ccl_t;
+typedef struct cvb200_ccl_result cvb200_ccl_result_t;
+typedef struct cvb200_ccl_range { int32_t a; int16_t start; int16_t end; } cvb200_ccl_range_t;          /* == compv_ccl_range_t (ccl_lsl_result.h:32-36): label, [start, end) */
+typedef struct cvb200_rect16 { int16_t left, top, right, bottom; } cvb200_rect16_t;                     /* == CompVRectInt16 (compv_common.h) */
+CVB200_API int cvb200_ccl_new(cvb200_ccl_t** ccl, int id /* CVB200_PLSL_ID */);
+CVB200_API int cvb200_ccl_free(cvb200_ccl_t** ccl);
+/* ccl_lsl.cxx:129-151: PLSL_SET_INT_TYPE (int, only XRLEZ), PLSL_SET_BOOL_SORT_SEGMENTS (bool); compv_ccl.cxx:25-40: CCL_SET_INT_CONNECTIVITY (int, 4 or 8; the LSL ignores it) */
+CVB200_API int cvb200_ccl_set(cvb200_ccl_t* ccl, int id, const void* valuePtr, size_t valueSize);
+/* binar: host. *result is reused when non-NULL (as the reference reuses *result of the same id, ccl_lsl.cxx:585-592), else created; free it with cvb200_ccl_result_free. */
+CVB200_API int cvb200_ccl_process(cvb200_ccl_t* ccl, const uint8_t* binar, size_t width, size_t height, size_t stride, cvb200_ccl_result_t** result);
+/* binar: device, `batch` frames. labels (device, may be NULL): batch x height x width int32, the flattened label image (debugFlatten); na (host, may be NULL): labels per frame;
+ * results (host array of `batch` handles, may be NULL): filled like cvb200_ccl_process does. */
+CVB200_API int cvb200_ccl_process_dev(cvb200_ccl_t* ccl, const uint8_t* binar, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
+	int32_t* labels, int32_t* na, cvb200_ccl_result_t** results, cvb200_stream_t stream);
+CVB200_API int cvb200_ccl_result_free(cvb200_ccl_result_t** result);
+/* labelsCount() (ccl_lsl_result.cxx:45-48); labelIds() are 1..count */
+CVB200_API size_t cvb200_ccl_result_labels_count(const cvb200_ccl_result_t* result);
+/* vecLEA() in CSR form: rowOffsets has height + 1 entries, ranges[rowOffsets[j] .. rowOffsets[j+1]) are row j's segments left to right. Pointers stay valid until the result is reused or freed. */
+CVB200_API int cvb200_ccl_result_segments(const cvb200_ccl_result_t* result, const uint32_t** rowOffsets, const cvb200_ccl_range_t** ranges, size_t* count);
+/* debugFlatten (ccl_lsl_result.cxx:51-98): labels is height rows of labelsStride int32 (host) */
+CVB200_API int cvb200_ccl_result_flatten(const cvb200_ccl_result_t* result, int32_t* labels, size_t labelsStride);
+/* boundingBoxes (ccl_lsl_result.cxx:136-185): right is the exclusive end column, bottom the last row */
+CVB200_API int cvb200_ccl_result_bounding_boxes(const cvb200_ccl_result_t* result, cvb200_rect16_t* boxes, size_t capacity, size_t* count);
 
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */

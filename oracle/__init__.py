@@ -293,6 +293,30 @@ def hough_sht(which, edges, rho=1.0, theta=1.0, threshold=1, max_lines=0, width=
     return (out, cnt.value, ms[:iters]) if iters else (out, cnt.value)
 
 
+RANGE_DTYPE = np.dtype([("a", np.int32), ("start", np.int16), ("end", np.int16)])
+
+
+def ccl_lsl(which, img, width=None, threads=1, iters=0):
+    """PLSL labelling.  Returns dict(labels=int32 (h, w), na=int, boxes=int16 (na, 4) {left, top, right, bottom}[, row_offsets, ranges for 'orc'][, ms])."""
+    w, h, stride = _frame_args(img, width)
+    labels = np.zeros((h, w), np.int32)
+    na = C.c_int32(0)
+    boxes = np.zeros((max(1, (w * h + 1) // 2), 4), np.int16)
+    if which == "orc":
+        row_off = np.zeros(h + 1, np.uint32)
+        ranges = np.zeros(max(1, (w + 1) // 2 * h), RANGE_DTYPE)
+        nr = C.c_size_t(0)
+        _chk(orc().orc_ccl_lsl(_p(img), _sz(w), _sz(h), _sz(stride), _p(labels), C.byref(na), _p(boxes), _sz(len(boxes)), _p(row_off), _p(ranges), _sz(len(ranges)),
+                               C.byref(nr)), "orc_ccl_lsl")
+        return dict(labels=labels, na=na.value, boxes=boxes[:na.value].copy(), row_offsets=row_off, ranges=ranges[:nr.value].copy())
+    ms = np.zeros(max(iters, 1), np.float64)
+    _chk(ref(threads).ref_ccl_lsl(_p(img), _sz(w), _sz(h), _sz(stride), _p(labels), C.byref(na), _p(boxes), _sz(len(boxes)), int(iters), _p(ms)), "ref_ccl_lsl")
+    out = dict(labels=labels, na=na.value, boxes=boxes[:na.value].copy())
+    if iters:
+        out["ms"] = ms[:iters]
+    return out
+
+
 def histogram(img, width=None):
     w, h, stride = _frame_args(img, width)
     hist = np.zeros(256, np.uint32)

@@ -406,4 +406,78 @@ void ref_edge_session_free(void* session)
 	delete static_cast<RefEdgeSession*>(session);
 }
 
+// ---- a11: CompVConnectedComponentLabeling (COMPV_PLSL_ID) through the factory (base/compv_ccl.cxx:69-97) ----
+// labels: height x width int32 (strideless, CompVConnectedComponentLabelingResultLSL::debugFlatten); boxes: labelsCount x {left, top, right, bottom} int16
+// (CompVRectInt16, boundingBoxes()). boxCap in boxes. iters > 0 adds a timed loop over process() only.
+int ref_ccl_lsl(const uint8_t* img, size_t w, size_t h, size_t stride, int32_t* labels, int32_t* naOut, int16_t* boxes, size_t boxCap, int iters, double* msOut)
+{
+	CompVMatPtr image;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVConnectedComponentLabelingPtr ccl;
+	SHIM_CHECK(CompVConnectedComponentLabeling::newObj(&ccl, COMPV_PLSL_ID));
+	CompVConnectedComponentLabelingResultPtr result;
+	SHIM_CHECK(ccl->process(image, &result));
+	for (int it = 0; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(ccl->process(image, &result));
+		if (msOut) msOut[it] = now_ms() - t0;
+	}
+	const CompVConnectedComponentLabelingResultLSL* lsl = CompVConnectedComponentLabeling::reinterpret_castr<CompVConnectedComponentLabelingResultLSL>(result);
+	if (!lsl) return -2;
+	if (naOut) *naOut = static_cast<int32_t>(lsl->labelsCount());
+	if (labels) {
+		if (lsl->labelsCount()) {
+			CompVMatPtr flat;
+			SHIM_CHECK(lsl->debugFlatten(&flat));
+			for (size_t j = 0; j < h; ++j) memcpy(labels + j * w, flat->ptr<const int32_t>(j), w * sizeof(int32_t));
+		}
+		else memset(labels, 0, w * h * sizeof(int32_t)); // black image: the result is empty (ccl_lsl.cxx:676-680), debugFlatten refuses it
+	}
+	if (boxes) {
+		CompVConnectedComponentBoundingBoxesVector bb;
+		SHIM_CHECK(lsl->boundingBoxes(bb));
+		static_assert(sizeof(CompVConnectedComponentBoundingBox) == 8, "CompVRectInt16 layout");
+		memcpy(boxes, bb.data(), (bb.size() < boxCap ? bb.size() : boxCap) * sizeof(CompVConnectedComponentBoundingBox));
+	}
+	return 0;
+}
+
+// ---- a12: CompVConnectedComponentLabeling (COMPV_LMSER_ID) ----
+// regions are returned in the reference's order: regionSizes[i] = number of points, regionBoxes[4*i..] = {left, top, right, bottom},
+// points (int16 x, y pairs) concatenated in region order up to pointCap points. *regionCount / *pointCount receive the totals.
+int ref_ccl_lmser(const uint8_t* img, size_t w, size_t h, size_t stride, int delta, double minArea, double maxArea, double maxVariation, double minDiversity, int connectivity,
+	int32_t* regionSizes, int16_t* regionBoxes, size_t regionCap, int16_t* points, size_t pointCap, size_t* regionCount, size_t* pointCount, int iters, double* msOut)
+{
+	CompVMatPtr image;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVConnectedComponentLabelingPtr ccl;
+	SHIM_CHECK(CompVConnectedComponentLabeling::newObj(&ccl, COMPV_LMSER_ID, delta, minArea, maxArea, maxVariation, minDiversity, connectivity));
+	CompVConnectedComponentLabelingResultPtr result;
+	SHIM_CHECK(ccl->process(image, &result));
+	for (int it = 0; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(ccl->process(image, &result));
+		if (msOut) msOut[it] = now_ms() - t0;
+	}
+	const CompVConnectedComponentLabelingResultLMSER* mser = CompVConnectedComponentLabeling::reinterpret_castr<CompVConnectedComponentLabelingResultLMSER>(result);
+	if (!mser) return -2;
+	const CompVConnectedComponentLabelingRegionMserVector& regions = mser->points();
+	size_t np = 0;
+	for (size_t i = 0; i < regions.size(); ++i) {
+		const CompVConnectedComponentLabelingRegionMser& reg = regions[i];
+		if (i < regionCap) {
+			if (regionSizes) regionSizes[i] = static_cast<int32_t>(reg.points.size());
+			if (regionBoxes) { regionBoxes[4 * i] = reg.boundingBox.left; regionBoxes[4 * i + 1] = reg.boundingBox.top; regionBoxes[4 * i + 2] = reg.boundingBox.right; regionBoxes[4 * i + 3] = reg.boundingBox.bottom; }
+		}
+		for (size_t k = 0; k < reg.points.size(); ++k, ++np) {
+			if (points && np < pointCap) { points[2 * np] = reg.points[k].x; points[2 * np + 1] = reg.points[k].y; }
+		}
+	}
+	if (regionCount) *regionCount = regions.size();
+	if (pointCount) *pointCount = np;
+	return 0;
+}
+
 } // extern "C"
