@@ -146,6 +146,7 @@ def main():
     import torch
     import torch.distributed as dist
     import compv_b200 as cvb
+    from compv_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU reference)")
@@ -157,7 +158,7 @@ def main():
 
     B = args.frames
     distinct = min(B, 64)
-    frames = np.concatenate([make_frames(distinct, 12345 + rank * 1000)] * ((B + distinct - 1) // distinct))[:B]  # (B, H, W) uint8: larger than the 126 MB L2
+    frames = np.concatenate([make_frames(distinct, shard.weak_seed(12345, rank))] * ((B + distinct - 1) // distinct))[:B]  # (B, H, W) uint8: larger than the 126 MB L2
     h_in = torch.from_numpy(frames).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
     d_in = h_in.cuda()
@@ -175,10 +176,10 @@ def main():
     def step_e2e():
         nlines[0] = sum(len(x) for x in cvb.canny_kht_process_batch(dete, kht, h_in.numpy(), width=W, capacity=512))
 
+    dev = torch.device("cuda", local_rank)
+
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        shard.barrier(dev)
 
     def timed(fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -190,12 +191,10 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
-        dev = e0.elapsed_time(e1)
+        dev_ms_ = e0.elapsed_time(e1)
         barrier()
-        t = torch.tensor([dev, wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
+        dev_max, wall_max = shard.max_over_ranks([dev_ms_, wall], dev)
+        return dev_max, wall_max
 
     # ---- device-resident throughput ----
     for _ in range(args.warmup):
@@ -212,9 +211,9 @@ def main():
     _, e2e_ms = timed(step_e2e, args.steps)   # the host call is synchronous: wall clock around it is the honest number
     clocks = sampler.stop() if rank == 0 else None
 
-    px_per_step = B * W * H * world
-    value = px_per_step * args.steps / (dev_ms * 1e-3) / 1e6
-    e2e_value = px_per_step * args.steps / (e2e_ms * 1e-3) / 1e6
+    value = shard.whole_job_throughput(B * W * H, args.steps, world, dev_ms) / 1e6
+    e2e_value = shard.whole_job_throughput(B * W * H, args.steps, world, e2e_ms) / 1e6
+    lines_all = shard.gather_counts(nlines[0], dev)
 
     # ---- roofline of the dominant kernel: per-kernel CUDA-event timing over extra steps (rank 0) ----
     roof, kernels = None, {}
@@ -264,9 +263,9 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int16 (+f32 blur)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "frames_per_gpu_per_step": B, "tLow": TLOW, "tHigh": THIGH,
-                       "kernSize": KS, "blur": [BLUR, SIGMA], "kht": {"rho": 1, "theta_deg": 1, "threshold": KHT_THRESHOLD}, "lines_per_step_rank0": nlines[0], "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6),
+                       "kernSize": KS, "blur": [BLUR, SIGMA], "kht": {"rho": 1, "theta_deg": 1, "threshold": KHT_THRESHOLD}, "lines_per_step_per_rank": lines_all, "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6),
                        "parallelism": "frames sharded across %d GPU(s), no collective" % world},
-            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": B * W * H * world, "d2h_bytes_per_step": nlines[0] * 16 * world,
+            "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": B * W * H * world, "d2h_bytes_per_step": sum(lines_all) * 16,
                     "ms_per_step": e2e_ms / args.steps, "api": "cvb200_canny_kht_process_batch (pinned host frames in, lines out)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
         }
