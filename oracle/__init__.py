@@ -317,6 +317,34 @@ def ccl_lsl(which, img, width=None, threads=1, iters=0):
     return out
 
 
+def ccl_lmser(which, img, delta=2, min_area=0.0055 * 0.0055, max_area=0.8 * 0.15, max_variation=0.3, min_diversity=0.2, connectivity=8, width=None, threads=1, iters=0,
+              point_cap=None):
+    """Linear-time MSER.  Defaults are the reference's unit-test parameters (unittests/ccl_mser.cxx:26-46).
+    Returns dict(sizes=int32 (n,), boxes=int16 (n, 4) {left, top, right, bottom}, points=list of (size, 2) int16 (x, y) arrays in the reference's order[, ms])."""
+    w, h, stride = _frame_args(img, width)
+    region_cap = w * h + 2
+    if point_cap is None:
+        point_cap = 64 * w * h
+    sizes = np.zeros(region_cap, np.int32)
+    boxes = np.zeros((region_cap, 4), np.int16)
+    pts = np.zeros((point_cap, 2), np.int16)
+    nr, npts = C.c_size_t(0), C.c_size_t(0)
+    args = [_p(img), _sz(w), _sz(h), _sz(stride), int(delta), C.c_double(min_area), C.c_double(max_area), C.c_double(max_variation), C.c_double(min_diversity), int(connectivity),
+            _p(sizes), _p(boxes), _sz(region_cap), _p(pts), _sz(point_cap), C.byref(nr), C.byref(npts)]
+    ms = np.zeros(max(iters, 1), np.float64)
+    if which == "orc":
+        _chk(orc().orc_ccl_lmser(*args), "orc_ccl_lmser")
+    else:
+        _chk(ref(threads).ref_ccl_lmser(*(args + [int(iters), _p(ms)])), "ref_ccl_lmser")
+    n = nr.value
+    assert npts.value <= point_cap, "point_cap too small: %d points" % npts.value
+    offs = np.concatenate([[0], np.cumsum(sizes[:n])])
+    out = dict(sizes=sizes[:n].copy(), boxes=boxes[:n].copy(), points=[pts[offs[i]:offs[i + 1]].copy() for i in range(n)])
+    if iters and which != "orc":
+        out["ms"] = ms[:iters]
+    return out
+
+
 def histogram(img, width=None):
     w, h, stride = _frame_args(img, width)
     hist = np.zeros(256, np.uint32)

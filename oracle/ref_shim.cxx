@@ -463,7 +463,7 @@ int ref_ccl_lmser(const uint8_t* img, size_t w, size_t h, size_t stride, int del
 	}
 	const CompVConnectedComponentLabelingResultLMSER* mser = CompVConnectedComponentLabeling::reinterpret_castr<CompVConnectedComponentLabelingResultLMSER>(result);
 	if (!mser) return -2;
-	const CompVConnectedComponentLabelingRegionMserVector& regions = mser->points();
+	const CompVConnectedComponentLabelingRegionMserVector& regions = mser->boundingBoxes(); // same vector as points(), with the boxes filled (lmser_result.cxx:50-88)
 	size_t np = 0;
 	for (size_t i = 0; i < regions.size(); ++i) {
 		const CompVConnectedComponentLabelingRegionMser& reg = regions[i];
