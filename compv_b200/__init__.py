@@ -283,6 +283,20 @@ class CompVConnectedComponentLabelingResult:
         buf = (C.c_char * (n.value * RANGE_DTYPE.itemsize)).from_address(rg.value)
         return row_offsets, np.frombuffer(buf, RANGE_DTYPE).copy()
 
+    def regions(self):
+        """LMSER results: dict(sizes int32 (n,), boxes int16 (n, 4), points list of (size, 2) int16 (x, y)) -- CompVConnectedComponentLabelingResultLMSER::points()."""
+        ps, pb, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nr, npts = C.c_size_t(0), C.c_size_t(0)
+        check(lib().cvb200_ccl_result_regions(self._h, C.byref(ps), C.byref(pb), C.byref(pp), C.byref(nr), C.byref(npts)), "cvb200_ccl_result_regions")
+        n, m = nr.value, npts.value
+        if not n:
+            return dict(sizes=np.zeros(0, np.int32), boxes=np.zeros((0, 4), np.int16), points=[])
+        sizes = np.frombuffer((C.c_char * (4 * n)).from_address(ps.value), np.int32).copy()
+        boxes = np.frombuffer((C.c_char * (8 * n)).from_address(pb.value), np.int16).reshape(n, 4).copy()
+        pts = np.frombuffer((C.c_char * (4 * m)).from_address(pp.value), np.int16).reshape(m, 2).copy()
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        return dict(sizes=sizes, boxes=boxes, points=[pts[offs[i]:offs[i + 1]] for i in range(n)])
+
     def debugFlatten(self):
         labels = np.zeros((self.height, self.width), np.int32)
         check(lib().cvb200_ccl_result_flatten(self._h, vp(labels), sz(self.width)), "cvb200_ccl_result_flatten")
@@ -309,9 +323,11 @@ class CompVConnectedComponentLabeling:
         self._h = handle
 
     @staticmethod
-    def newObj(ccl_id=_ffi.PLSL_ID):
+    def newObj(ccl_id=_ffi.PLSL_ID, delta=5, min_area=0.0002, max_area=0.5, max_variation=0.5, min_diversity=0.5, connectivity=8):
+        """CompVConnectedComponentLabeling::newObj (compv_ccl.h:229-236), same defaults."""
         h = C.c_void_p()
-        check(lib().cvb200_ccl_new(C.byref(h), int(ccl_id)), "cvb200_ccl_new")
+        check(lib().cvb200_ccl_new_ex(C.byref(h), int(ccl_id), int(delta), C.c_double(min_area), C.c_double(max_area), C.c_double(max_variation), C.c_double(min_diversity),
+                                      int(connectivity)), "cvb200_ccl_new_ex")
         return CompVConnectedComponentLabeling(h)
 
     def set(self, cap_id, value, ctype):

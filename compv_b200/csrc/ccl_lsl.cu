@@ -15,7 +15,7 @@
 //                 Frames of a batch run concurrently on different SMs.
 //   lsl_resolve   step 4 (EQ -> final numbering): roots ranked with a block scan, other labels chase EQ to their root (equal to the serial A[ea] = A[EQ[ea]])
 //   lsl_lea       final label per segment -> the LEA {a, start, end}; lsl_flatten: label image straight from the bitmap rank (no per-run loops)
-#include "common.cuh"
+#include "ccl.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -306,23 +306,6 @@ __global__ void __launch_bounds__(256) lsl_flatten_kernel(const unsigned int* __
 
 using namespace cvb;
 
-struct cvb200_ccl_result {
-	size_t width = 0, height = 0;
-	int32_t na = 0;
-	std::vector<uint32_t> rowOffsets;
-	std::vector<cvb200_ccl_range_t> ranges;
-};
-
-struct cvb200_ccl {
-	int id;
-	int type;
-	bool sortSegments;
-	int connectivity;
-	DevBuf fg, spre, rowCnt, rowOff, frames, segStart, segEnd, ov, label, eq, a, ranges, hostIn;
-	HostBuf hFrames, hRowOff, hRanges;
-	std::mutex mutex;
-};
-
 static int lsl_process_dev(cvb200_ccl* c, const uint8_t* binar, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
 	int32_t* labels, int32_t* na, cvb200_ccl_result_t** results, cudaStream_t stream)
 {
@@ -425,7 +408,8 @@ static int lsl_process_dev(cvb200_ccl* c, const uint8_t* binar, size_t width, si
 		if (results) {
 			if (!results[f]) { results[f] = new (std::nothrow) cvb200_ccl_result(); CVB_REQUIRE(results[f], CVB200_E_OUT_OF_MEMORY); }
 			cvb200_ccl_result* r = results[f];
-			r->width = width; r->height = height; r->na = hf[f].na;
+			r->id = CVB200_PLSL_ID; r->width = width; r->height = height; r->na = hf[f].na;
+			r->regionSizes.clear(); r->regionBoxes.clear(); r->regionPoints.clear();
 			const uint32_t* ro = c->hRowOff.as<uint32_t>() + f * (height + 1);
 			r->rowOffsets.assign(ro, ro + height + 1);
 			const cvb200_ccl_range_t* rg = total ? c->hRanges.as<cvb200_ccl_range_t>() + hf[f].segBase : nullptr;
@@ -437,23 +421,34 @@ static int lsl_process_dev(cvb200_ccl* c, const uint8_t* binar, size_t width, si
 
 extern "C" {
 
-int cvb200_ccl_new(cvb200_ccl_t** ccl, int id)
+// CompVConnectedComponentLabeling::newObj (base/compv_ccl.cxx:69-97): same parameter checks, same defaults (compv_ccl.h:23-28)
+int cvb200_ccl_new_ex(cvb200_ccl_t** ccl, int id, int delta, double minArea, double maxArea, double maxVariation, double minDiversity, int connectivity)
 {
-	CVB_REQUIRE(ccl, CVB200_E_INVALID_PARAMETER);
 	CVB_REQUIRE_INIT();
-	CVB_REQUIRE(id == CVB200_PLSL_ID, CVB200_E_INVALID_PARAMETER); // compv_ccl.cxx:83-87: unknown factory id
+	CVB_REQUIRE(ccl && delta > 0 && delta <= 255 && minArea >= 0.0 && minArea <= 1.0 && minArea <= maxArea && maxArea >= 0.0 && maxArea <= 1.0
+		&& maxVariation >= 0.0 && maxVariation <= 1.0 && minDiversity >= 0.0 && minDiversity <= 1.0 && (connectivity == 4 || connectivity == 8), CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(id == CVB200_PLSL_ID || id == CVB200_LMSER_ID, CVB200_E_INVALID_PARAMETER); // :83-87: unknown factory id
 	cvb200_ccl* c = new (std::nothrow) cvb200_ccl();
 	CVB_REQUIRE(c, CVB200_E_OUT_OF_MEMORY);
-	c->id = id; c->type = CVB200_PLSL_TYPE_XRLEZ; c->sortSegments = false; c->connectivity = 8; // ccl_lsl.cxx:118-124, compv_ccl.h:28
+	c->id = id; c->type = CVB200_PLSL_TYPE_XRLEZ; c->sortSegments = false; // ccl_lsl.cxx:118-124
+	c->delta = delta; c->minArea = minArea; c->maxArea = maxArea; c->maxVariation = maxVariation; c->minDiversity = minDiversity; c->connectivity = connectivity;
 	*ccl = c;
 	return CVB200_S_OK;
+}
+
+int cvb200_ccl_new(cvb200_ccl_t** ccl, int id)
+{
+	return cvb200_ccl_new_ex(ccl, id, 5, 0.0002, 0.5, 0.5, 0.5, 8);
 }
 
 int cvb200_ccl_free(cvb200_ccl_t** ccl)
 {
 	if (ccl && *ccl) {
 		cvb200_ccl* c = *ccl;
-		DevBuf* bufs[] = { &c->fg, &c->spre, &c->rowCnt, &c->rowOff, &c->frames, &c->segStart, &c->segEnd, &c->ov, &c->label, &c->eq, &c->a, &c->ranges, &c->hostIn };
+		DevBuf* bufs[] = { &c->fg, &c->spre, &c->rowCnt, &c->rowOff, &c->frames, &c->segStart, &c->segEnd, &c->ov, &c->label, &c->eq, &c->a, &c->ranges, &c->hostIn,
+			&c->mUf, &c->mStamp, &c->mPending, &c->mCompSize, &c->mAddSize, &c->mOwnCnt, &c->mTopNode, &c->mPixNode, &c->mOrder, &c->mAbsorbed, &c->mNodeRoot, &c->mNodeParent,
+			&c->mNodeArea, &c->mNodeOwn, &c->mNodeLevel, &c->mChild, &c->mSister, &c->mOff, &c->mCursor, &c->mOwnCursor, &c->mVar, &c->mFlags, &c->mDfsPix, &c->mCounters, &c->mRegions,
+			&c->mOutOff, &c->mPoints, &c->mBoxes };
 		for (DevBuf* b : bufs) b->release();
 		c->hFrames.release(); c->hRowOff.release(); c->hRanges.release();
 		delete c;
@@ -468,17 +463,19 @@ int cvb200_ccl_set(cvb200_ccl_t* c, int id, const void* valuePtr, size_t valueSi
 	CVB_REQUIRE(c && valuePtr && valueSize, CVB200_E_INVALID_PARAMETER);
 	switch (id) {
 	case CVB200_PLSL_SET_INT_TYPE:
+		CVB_REQUIRE(c->id == CVB200_PLSL_ID, CVB200_E_NOT_IMPLEMENTED); // the LMSER forwards everything to the base class (ccl_lmser.cxx:138-146)
 		CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
 		CVB_REQUIRE(*static_cast<const int*>(valuePtr) == CVB200_PLSL_TYPE_XRLEZ, CVB200_E_NOT_IMPLEMENTED);
 		c->type = *static_cast<const int*>(valuePtr); return CVB200_S_OK;
 	case CVB200_PLSL_SET_BOOL_SORT_SEGMENTS:
+		CVB_REQUIRE(c->id == CVB200_PLSL_ID, CVB200_E_NOT_IMPLEMENTED);
 		CVB_REQUIRE(valueSize == sizeof(bool), CVB200_E_INVALID_PARAMETER);
 		c->sortSegments = *static_cast<const bool*>(valuePtr); return CVB200_S_OK;
 	case CVB200_CCL_SET_INT_CONNECTIVITY: {
 		CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
 		const int v = *static_cast<const int*>(valuePtr);
 		CVB_REQUIRE(v == 4 || v == 8, CVB200_E_NOT_IMPLEMENTED);
-		c->connectivity = v; return CVB200_S_OK; // stored, not used: the LSL is 8-connected whatever the value (ccl_lsl.cxx:361-363)
+		c->connectivity = v; return CVB200_S_OK; // the LSL is 8-connected whatever the value (ccl_lsl.cxx:361-363); the LMSER uses it (ccl_lmser.cxx:172-192)
 	}
 	default:
 		return CVB200_E_NOT_IMPLEMENTED;
@@ -494,6 +491,12 @@ int cvb200_ccl_process_dev(cvb200_ccl_t* c, const uint8_t* binar, size_t width, 
 	if (!framePitch) framePitch = stride * height;
 	CVB_REQUIRE(framePitch >= stride * height, CVB200_E_INVALID_PARAMETER);
 	std::lock_guard<std::mutex> lock(c->mutex);
+	if (c->id == CVB200_LMSER_ID) {
+		CVB_REQUIRE(!labels, CVB200_E_NOT_IMPLEMENTED); // debugFlatten is not implemented for MSER results (lmser_result.cxx:35-39)
+		CVB_CHECK(mser_process_dev(c, binar, width, height, stride, batch, framePitch, results, as_stream(stream)));
+		if (na) for (size_t f = 0; f < batch; ++f) na[f] = results[f]->na;
+		return CVB200_S_OK;
+	}
 	return lsl_process_dev(c, binar, width, height, stride, batch, framePitch, labels, na, results, as_stream(stream));
 }
 
@@ -521,6 +524,7 @@ size_t cvb200_ccl_result_labels_count(const cvb200_ccl_result_t* result) { retur
 int cvb200_ccl_result_segments(const cvb200_ccl_result_t* result, const uint32_t** rowOffsets, const cvb200_ccl_range_t** ranges, size_t* count)
 {
 	CVB_REQUIRE(result, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(result->id == CVB200_PLSL_ID, CVB200_E_NOT_IMPLEMENTED);
 	if (rowOffsets) *rowOffsets = result->rowOffsets.data();
 	if (ranges) *ranges = result->ranges.data();
 	if (count) *count = result->ranges.size();
@@ -531,6 +535,7 @@ int cvb200_ccl_result_segments(const cvb200_ccl_result_t* result, const uint32_t
 int cvb200_ccl_result_flatten(const cvb200_ccl_result_t* result, int32_t* labels, size_t labelsStride)
 {
 	CVB_REQUIRE(result && labels && labelsStride >= result->width, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(result->id == CVB200_PLSL_ID, CVB200_E_NOT_IMPLEMENTED); // lmser_result.cxx:35-39
 	CVB_REQUIRE(result->width && result->height && result->rowOffsets.size() == result->height + 1, CVB200_E_INVALID_STATE);
 	for (size_t j = 0; j < result->height; ++j) {
 		int32_t* row = labels + j * labelsStride;
@@ -551,6 +556,10 @@ int cvb200_ccl_result_bounding_boxes(const cvb200_ccl_result_t* result, cvb200_r
 	*count = na;
 	if (!na || !capacity) return CVB200_S_OK;
 	const size_t n = std::min(na, capacity);
+	if (result->id == CVB200_LMSER_ID) { // lmser_result.cxx:50-88: inclusive min / max of the region's points
+		memcpy(boxes, result->regionBoxes.data(), n * sizeof(cvb200_rect16_t));
+		return CVB200_S_OK;
+	}
 	for (size_t k = 0; k < n; ++k) { boxes[k].left = static_cast<int16_t>(result->width); boxes[k].top = static_cast<int16_t>(result->height); boxes[k].right = 0; boxes[k].bottom = 0; }
 	for (size_t j = 0; j < result->height; ++j) {
 		const int16_t y = static_cast<int16_t>(j);
@@ -565,6 +574,19 @@ int cvb200_ccl_result_bounding_boxes(const cvb200_ccl_result_t* result, cvb200_r
 			bb.bottom = y;
 		}
 	}
+	return CVB200_S_OK;
+}
+
+// CompVConnectedComponentLabelingResultLMSER::points() (compv_ccl.h:159-170): sizes[i] points per region, boxes[i], points = (x, y) int16 pairs, regions back to back
+int cvb200_ccl_result_regions(const cvb200_ccl_result_t* result, const int32_t** sizes, const cvb200_rect16_t** boxes, const int16_t** points, size_t* regionCount, size_t* pointCount)
+{
+	CVB_REQUIRE(result, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(result->id == CVB200_LMSER_ID, CVB200_E_NOT_IMPLEMENTED);
+	if (sizes) *sizes = result->regionSizes.data();
+	if (boxes) *boxes = result->regionBoxes.data();
+	if (points) *points = result->regionPoints.data();
+	if (regionCount) *regionCount = result->regionSizes.size();
+	if (pointCount) *pointCount = result->regionPoints.size() / 2;
 	return CVB200_S_OK;
 }
 

@@ -307,7 +307,9 @@ typedef struct cvb200_ccl cvb200_ccl_t;
 typedef struct cvb200_ccl_result cvb200_ccl_result_t;
 typedef struct cvb200_ccl_range { int32_t a; int16_t start; int16_t end; } cvb200_ccl_range_t;          /* == compv_ccl_range_t (ccl_lsl_result.h:32-36): label, [start, end) */
 typedef struct cvb200_rect16 { int16_t left, top, right, bottom; } cvb200_rect16_t;                     /* == CompVRectInt16 (compv_common.h) */
-CVB200_API int cvb200_ccl_new(cvb200_ccl_t** ccl, int id /* CVB200_PLSL_ID */);
+CVB200_API int cvb200_ccl_new(cvb200_ccl_t** ccl, int id /* CVB200_PLSL_ID or CVB200_LMSER_ID */);
+/* the full CompVConnectedComponentLabeling::newObj signature (compv_ccl.h:229-236); the MSER parameters are ignored by the PLSL */
+CVB200_API int cvb200_ccl_new_ex(cvb200_ccl_t** ccl, int id, int delta, double minArea, double maxArea, double maxVariation, double minDiversity, int connectivity);
 CVB200_API int cvb200_ccl_free(cvb200_ccl_t** ccl);
 /* ccl_lsl.cxx:129-151: PLSL_SET_INT_TYPE (int, only XRLEZ), PLSL_SET_BOOL_SORT_SEGMENTS (bool); compv_ccl.cxx:25-40: CCL_SET_INT_CONNECTIVITY (int, 4 or 8; the LSL ignores it) */
 CVB200_API int cvb200_ccl_set(cvb200_ccl_t* ccl, int id, const void* valuePtr, size_t valueSize);
@@ -326,6 +328,16 @@ CVB200_API int cvb200_ccl_result_segments(const cvb200_ccl_result_t* result, con
 CVB200_API int cvb200_ccl_result_flatten(const cvb200_ccl_result_t* result, int32_t* labels, size_t labelsStride);
 /* boundingBoxes (ccl_lsl_result.cxx:136-185): right is the exclusive end column, bottom the last row */
 CVB200_API int cvb200_ccl_result_bounding_boxes(const cvb200_ccl_result_t* result, cvb200_rect16_t* boxes, size_t capacity, size_t* count);
+
+/* ================================================================================================
+ * a12 -- maximally stable extremal regions. Replaces CompVConnectedComponentLabeling::newObj(&ccl, COMPV_LMSER_ID, delta, min_area, max_area, max_variation, min_diversity, connectivity)
+ * + ccl->process(gray, &result) (core/ccl/compv_core_ccl_lmser.cxx:148-410) and CompVConnectedComponentLabelingResultLMSER::points() / boundingBoxes() (compv_ccl.h:159-170).
+ * Same object and calls as a11 (cvb200_ccl_new_ex, cvb200_ccl_process[_dev] with labels == NULL); the stride is part of the input: like the reference, pixel indices
+ * i and i +- 1 are neighbours wherever both are pixels, so with stride == width the end of a row touches the start of the next (ccl_lmser.cxx:214-231).
+ * The same REGIONS as the reference (same pixel sets, same boxes); they are returned sorted by (grey level, smallest pixel index) and the order of the points inside a
+ * region is unspecified -- the reference's orders are those of its serial flood.
+ * ============================================================================================== */
+CVB200_API int cvb200_ccl_result_regions(const cvb200_ccl_result_t* result, const int32_t** sizes, const cvb200_rect16_t** boxes, const int16_t** points, size_t* regionCount, size_t* pointCount);
 
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
