@@ -57,10 +57,42 @@ __device__ __forceinline__ int uf_find(int* __restrict__ uf, int x)
 	return x;
 }
 
-__global__ void mser_init_kernel(int* uf, int* stamp, int* topNode, int* compSize, int* addSize, int* ownCnt, MserGeom g)
+__global__ void mser_init_kernel(int* stamp, int* topNode, int* compSize, int* addSize, int* ownCnt, MserGeom g)
 {
 	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.total; i += (long long)gridDim.x * blockDim.x) {
-		uf[i] = static_cast<int>(i); stamp[i] = -1; topNode[i] = -1; compSize[i] = 0; addSize[i] = 0; ownCnt[i] = 0;
+		stamp[i] = -1; topNode[i] = -1; compSize[i] = 0; addSize[i] = 0; ownCnt[i] = 0;
+	}
+}
+
+// Union-find initialisation, one block per image row: every pixel starts attached to the first pixel of its maximal run of equal grey level in the row.
+// Those pixels become active at the same level and are 4-connected, so the horizontal unions of flat areas are done before the level loop starts
+// (the run start is the smallest index of the run: it stays the root).  Until their level is reached nobody looks at them.
+__global__ void __launch_bounds__(256) mser_runstart_kernel(const uint8_t* __restrict__ img, int* __restrict__ uf, MserGeom g)
+{
+	__shared__ int sWarp[8];
+	__shared__ int sCarry;
+	const int y = blockIdx.x, f = blockIdx.y;
+	const uint8_t* row = img + static_cast<size_t>(f) * g.framePitch + static_cast<size_t>(y) * g.S;
+	int* ufRow = uf + (static_cast<size_t>(f) * g.H + y) * g.S;
+	const int rowBase = (f * g.H + y) * g.S;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) sCarry = 0;
+	__syncthreads();
+	for (int x0 = 0; x0 < g.S; x0 += 256) {
+		const int x = x0 + threadIdx.x;
+		int v = -1; // column where a run starts, else -1
+		if (x < g.W && (x == 0 || row[x - 1] != row[x])) v = x;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v = max(v, u); }
+		if (lane == 31) sWarp[warp] = v;
+		__syncthreads();
+		int pre = sCarry;
+		for (int w = 0; w < warp; ++w) pre = max(pre, sWarp[w]);
+		v = max(v, pre);
+		if (x < g.S) ufRow[x] = rowBase + ((x < g.W) ? v : x);
+		__syncthreads();
+		if (threadIdx.x == 255) sCarry = v;
+		__syncthreads();
 	}
 }
 
@@ -132,6 +164,7 @@ __global__ void __launch_bounds__(MSER_BLOCK) mser_union_kernel(const uint8_t* _
 			if (!mser_valid(g, q)) continue;
 			const int lq = frame[q];
 			if (lq > t || (lq == t && q > idx)) continue; // higher levels later; equal levels are united once, from the larger index
+			if (lq == t && q == idx - 1 && (idx % g.S) != 0) continue; // same row run: united by mser_runstart
 			int ra = uf_find(uf, p), rb = uf_find(uf, f * FP + q);
 			while (ra != rb) {
 				if (ra < rb) { const int tmp = ra; ra = rb; rb = tmp; }
@@ -152,11 +185,15 @@ __global__ void __launch_bounds__(MSER_BLOCK) mser_claim_kernel(const int* __res
 	for (unsigned int i = i0 + blockIdx.x * MSER_BLOCK + threadIdx.x; i < i1; i += gridDim.x * MSER_BLOCK) {
 		const int p = order[i];
 		const int r = uf_find(uf, p);
-		atomicAdd(&ownCnt[r], 1);
-		if (atomicExch(&stamp[r], t) != t) {
-			const int n = static_cast<int>(atomicAdd(&cnt->nodeCount, 1u));
-			nodeRoot[n] = r;
-			pendingNode[r] = n;
+		// lanes of the warp that found the same root speak once (flat areas put whole warps on one root)
+		const unsigned int peers = __match_any_sync(__activemask(), r);
+		if ((__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31)) {
+			atomicAdd(&ownCnt[r], __popc(peers));
+			if (atomicExch(&stamp[r], t) != t) {
+				const int n = static_cast<int>(atomicAdd(&cnt->nodeCount, 1u));
+				nodeRoot[n] = r;
+				pendingNode[r] = n;
+			}
 		}
 	}
 }
@@ -291,7 +328,12 @@ __global__ void mser_layout_kernel(const int* __restrict__ order, const int* __r
 		const int idx = p % FP;
 		const short y = static_cast<short>(__fmul_rn(static_cast<float>(idx), g.strideScale)); // computeFinalPoints :145-146, float arithmetic included
 		const short x = static_cast<short>(idx - (y * g.S));
-		dfsPix[off[n] + atomicAdd(&ownCursor[n], 1)] = make_short2(x, y);
+		const unsigned int peers = __match_any_sync(__activemask(), n);
+		const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+		int base = 0;
+		if (lane == leader) base = atomicAdd(&ownCursor[n], __popc(peers));
+		base = __shfl_sync(peers, base, leader);
+		dfsPix[off[n] + base + __popc(peers & ((1u << lane) - 1u))] = make_short2(x, y);
 	}
 }
 
@@ -368,8 +410,9 @@ static int mser_chunk(cvb200_ccl* c, const uint8_t* img, size_t width, size_t he
 
 	CVB_CUDA(cudaMemsetAsync(dCnt, 0, sizeof(MserCounters) + 256 * 4, stream));
 	{ KernelScope ks_("mser_init", stream);
-	  mser_init_kernel<<<MSER_GRID, 256, 0, stream>>>(uf, c->mStamp.as<int>(), c->mTopNode.as<int>(), c->mCompSize.as<int>(), c->mAddSize.as<int>(), c->mOwnCnt.as<int>(), g); }
-	CVB_LAUNCHED();
+	  mser_init_kernel<<<MSER_GRID, 256, 0, stream>>>(c->mStamp.as<int>(), c->mTopNode.as<int>(), c->mCompSize.as<int>(), c->mAddSize.as<int>(), c->mOwnCnt.as<int>(), g);
+	  mser_runstart_kernel<<<dim3(static_cast<unsigned>(height), static_cast<unsigned>(batch)), 256, 0, stream>>>(img, uf, g); }
+	CVB_LAUNCHED(); g_launches.fetch_add(1, std::memory_order_relaxed);
 	{ KernelScope ks_("mser_sort", stream);
 	  mser_hist_kernel<<<MSER_GRID, 256, 0, stream>>>(img, dCnt, g);
 	  mser_levelscan_kernel<<<1, 32, 0, stream>>>(dCnt, dLevelCursor);

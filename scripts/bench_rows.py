@@ -113,7 +113,7 @@ def row_lsl(args):
 def row_mser(args):
     import oracle
     batch = min(args.batch, 8)
-    frames = np.stack([frame_text(W, H, 20 + k) for k in range(batch)])
+    frames = np.stack([frame_g(W, H, 20 + k) for k in range(batch)])
     d_in = torch.from_numpy(frames).cuda()
     ccl = cvb.CompVConnectedComponentLabeling.newObj(_ffi.LMSER_ID, delta=2, min_area=0.0055 * 0.0055, max_area=0.8 * 0.15, max_variation=0.3, min_diversity=0.2, connectivity=8)
     stream = torch.cuda.current_stream().cuda_stream
@@ -122,7 +122,7 @@ def row_mser(args):
     def step():
         na[:] = ccl.process_dev(d_in, W, H, W, batch=batch, want_results=True, stream=stream)[0]
     ms = timed(step, max(2, args.steps // 2), warmup=1)
-    extra = {"workload": "lmser_1080p text frame, delta=2 (unittests/ccl_mser.cxx parameters), regions + points returned to the host", "regions_frame0": int(na[0]),
+    extra = {"workload": "lmser_1080p frame G, delta=2 (unittests/ccl_mser.cxx parameters), regions + points returned to the host", "regions_frame0": int(na[0]),
              "kernels_ms": kernel_split(step, 2)}
     if oracle.have_ref():
         r = oracle.ccl_lmser("ref", frames[0], threads=-1, iters=2)
