@@ -28,7 +28,7 @@
 namespace cvb {
 
 struct KhtGeom {
-	int W, H, WW;              // WW = bitmap words per row
+	int W, H, WW;              // WW = bitmap words per row = ceil(W/32) + 1: the last word is always zero; a frame's bitmap has H + 2 rows (a zero row above and below)
 	size_t stride, framePitch;
 	unsigned int nRho, nTheta, cs; // cs = accumulator pitch (nRho + 2)
 	double dRho, dThetaDeg, rhoMaxNeg, halfW, halfH;
@@ -69,7 +69,7 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 		else {
 			for (int j = 0; j < 32 && x0 + j < g.W; ++j) if (row[x0 + j]) word |= 1u << j;
 		}
-		bits[(static_cast<size_t>(frame) * g.H + y) * g.WW + wi] = word;
+		bits[(static_cast<size_t>(frame) * (g.H + 2) + y + 1) * g.WW + wi] = word;
 	}
 	unsigned int c = __popc(word);
 	for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -77,54 +77,86 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 }
 
 // ---- linking ------------------------------------------------------------------------------------
-// Measured alternatives (bench_r1_c..f, frame G, 82k edge px, 5.9k walks per 1080p frame): this version 20.8 ms; shared-memory band caches of the
-// bitmap 30-47 ms.  The walk is a single dependent instruction chain on one lane, so its cost is (instructions per step) x (issue latency), not
-// memory: the variant with the fewest instructions wins.  Every access to a frame's bitmap comes from this one warp, so its SM's L1 stays coherent.
-// 3 neighbour bits (x-1, x, x+1) of a bitmap row -> bit0, bit1, bit2; out-of-image columns read as 0
-__device__ __forceinline__ unsigned int row3(const unsigned int* row, int x, int WW)
+// The walk is a single dependent instruction chain on one lane: its cost is (instructions per step) x (issue latency, ~4 cycles).  Measured on frame G
+// (82k edge px, 5.9k walks per 1080p frame): three bitmap row loads per step 20.8 ms (~110 instr/step); shared-memory band caches 30-47 ms; a 3-row x 64-column
+// register window with bounds checks 16.0 ms (91 instr/step, ncu r1c).  This version removes the bounds checks with a zero-padded bitmap (one extra row above
+// and below, one extra word per row), keeps running pointers instead of recomputing 64-bit addresses, and picks the next pixel with one find-first-set over
+// the 8 neighbour bits in the order of Algorithm 6 (houghkht.cxx:666-703: TL, T, TR, L, R, BL, B, BR) and two packed look-up constants.
+// Every access to a frame's bitmap comes from this one warp, so its SM's L1 stays coherent with the stores.
+struct KhtWalk {
+	unsigned long long t, c, b; // bitmap rows y-1, y, y+1, columns [32*wb, 32*wb + 64)
+	unsigned int* cptr;         // &row(y)[wb]
+	int rel;                    // x - 32*wb
+	int x, y;
+};
+
+__device__ __forceinline__ unsigned long long kht_ld64(const unsigned int* p)
 {
-	const int wi = x >> 5, b = x & 31;
-	const unsigned int w = row[wi];
-	if (b >= 1 && b <= 30) return (w >> (b - 1)) & 7u;
-	if (b == 0) return ((w & 3u) << 1) | (wi > 0 ? (row[wi - 1] >> 31) : 0u);
-	return ((w >> 30) & 3u) | ((wi + 1 < WW ? (row[wi + 1] & 1u) : 0u) << 2);
+	return static_cast<unsigned long long>(p[0]) | (static_cast<unsigned long long>(p[1]) << 32);
 }
 
-// Algorithm 6 (houghkht.cxx:666-703): first set neighbour in the order TL, T, TR, L, R, BL, B, BR. Rows outside the image do not exist.
-__device__ __forceinline__ bool kht_next(const unsigned int* bits, int& x, int& y, int H, int WW)
+__device__ __forceinline__ void kht_walk_load(KhtWalk& w, unsigned int* __restrict__ bits /* row 0 of the frame */, int WW)
 {
-	const unsigned int* rc = bits + static_cast<size_t>(y) * WW;
-	const unsigned int t = (y > 0) ? row3(rc - WW, x, WW) : 0u;
-	const unsigned int c = row3(rc, x, WW);
-	const unsigned int b = (y + 1 < H) ? row3(rc + WW, x, WW) : 0u;
-	if (t) { const int d = (t & 1u) ? -1 : ((t & 2u) ? 0 : 1); x += d; --y; return true; }
-	if (c & 1u) { --x; return true; }
-	if (c & 4u) { ++x; return true; }
-	if (b) { const int d = (b & 1u) ? -1 : ((b & 2u) ? 0 : 1); x += d; ++y; return true; }
-	return false;
+	const int wi = w.x >> 5;
+	const int wb = ((w.x & 31) < 16 && wi > 0) ? wi - 1 : wi; // x stays >= 16 columns away from both window edges (image borders excepted); wb + 1 <= WW - 1
+	w.rel = w.x - (wb << 5);
+	w.cptr = bits + static_cast<ptrdiff_t>(w.y) * WW + wb;
+	w.t = kht_ld64(w.cptr - WW);
+	w.c = kht_ld64(w.cptr);
+	w.b = kht_ld64(w.cptr + WW);
+}
+
+// erase the current pixel in the registers and in memory
+__device__ __forceinline__ void kht_walk_erase(KhtWalk& w)
+{
+	w.c &= ~(1ull << w.rel);
+	const int hi = w.rel >> 5;
+	w.cptr[hi] = hi ? static_cast<unsigned int>(w.c >> 32) : static_cast<unsigned int>(w.c);
+}
+
+// move to the next pixel of the string; false when the current pixel has no neighbour left
+__device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* __restrict__ bits, int WW)
+{
+	// bits x-1, x, x+1 of each row; rel == 0 only happens at the image's left border (the column left of it does not exist)
+	const int sh = w.rel - 1;
+	const unsigned int t3 = static_cast<unsigned int>(sh >= 0 ? (w.t >> sh) : (w.t << 1)) & 7u;
+	const unsigned int c3 = static_cast<unsigned int>(sh >= 0 ? (w.c >> sh) : (w.c << 1)) & 5u;
+	const unsigned int b3 = static_cast<unsigned int>(sh >= 0 ? (w.b >> sh) : (w.b << 1)) & 7u;
+	// TL T TR L R BL B BR -> bits 0..7
+	const unsigned int m = t3 | ((c3 & 1u) << 3) | ((c3 & 4u) << 2) | (b3 << 5);
+	if (!m) return false;
+	const int k2 = (__ffs(m) - 1) << 1;
+	const int dx = static_cast<int>((0x9224u >> k2) & 3u) - 1;  // dx + 1 for k = 0..7: 0 1 2 0 2 0 1 2
+	const int dy = static_cast<int>((0xa940u >> k2) & 3u) - 1;  // dy + 1 for k = 0..7: 0 0 0 1 1 2 2 2
+	w.x += dx; w.y += dy; w.rel += dx;
+	// leaving the window horizontally: only possible away from the image borders (wb > 0 on the left, more words on the right)
+	if ((w.rel < 1 && w.x > 0) || (w.rel > 62 && (w.x >> 5) + 1 < WW - 1)) { kht_walk_load(w, bits, WW); return true; }
+	if (dy < 0) { w.cptr -= WW; w.b = w.c; w.c = w.t; w.t = kht_ld64(w.cptr - WW); }
+	else if (dy > 0) { w.cptr += WW; w.t = w.c; w.c = w.b; w.b = kht_ld64(w.cptr + WW); }
+	return true;
 }
 
 __global__ void __launch_bounds__(32)
 kht_link_kernel(unsigned int* __restrict__ bitsAll, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
 {
 	const int frame = blockIdx.x, lane = threadIdx.x;
-	unsigned int* bits = bitsAll + static_cast<size_t>(frame) * g.H * g.WW;
+	const int W = g.W, H = g.H, WW = g.WW;
+	unsigned int* bits = bitsAll + (static_cast<size_t>(frame) * (H + 2) + 1) * WW; // row 0 of the frame (row -1 and row H are zero)
 	KhtFrame& fr = frames[frame];
 	ushort2* poss = possAll + fr.posOff;
 	uint2* strings = stringsAll + fr.strOff;
 	unsigned int nPos = 0, nStr = 0; // meaningful on lane 0
-	const int W = g.W, H = g.H, WW = g.WW;
+	const int lastWord = (W - 1) >> 5;
 
 	for (int y = 1; y < H - 1; ++y) {
 		unsigned int* row = bits + static_cast<size_t>(y) * WW;
-		for (int wb = 0; wb < WW; wb += 32) {
+		for (int wb = 0; wb <= lastWord; wb += 32) {
 			while (true) {
 				const int wi = wb + lane;
-				unsigned int w = (wi < WW) ? row[wi] : 0u;
+				unsigned int w = (wi <= lastWord) ? row[wi] : 0u;
 				// seeds are interior columns only: x in [1, W-2]
 				if (wi == 0) w &= ~1u;
-				if (wi == ((W - 1) >> 5)) w &= ~(1u << ((W - 1) & 31));
-				if (wi > ((W - 1) >> 5)) w = 0;
+				if (wi == lastWord) w &= ~(1u << ((W - 1) & 31));
 				const unsigned int any = __ballot_sync(0xffffffffu, w != 0);
 				if (!any) break;
 				const int src = __ffs(any) - 1;
@@ -134,19 +166,24 @@ kht_link_kernel(unsigned int* __restrict__ bitsAll, ushort2* __restrict__ possAl
 				if (lane == 0) {
 					// Algorithm 5 (houghkht.cxx:706-760)
 					begin = nPos;
-					int x = xr, yy = y;
+					ushort2* out = poss + nPos;
+					KhtWalk wk;
+					wk.x = xr; wk.y = y;
+					kht_walk_load(wk, bits, WW);
 					do {
-						poss[nPos++] = make_ushort2(static_cast<unsigned short>(x), static_cast<unsigned short>(yy));
-						bits[static_cast<size_t>(yy) * WW + (x >> 5)] &= ~(1u << (x & 31));
-					} while (kht_next(bits, x, yy, H, WW));
-					rev = nPos;
-					x = xr; yy = y;
-					if (kht_next(bits, x, yy, H, WW)) {
+						*out++ = make_ushort2(static_cast<unsigned short>(wk.x), static_cast<unsigned short>(wk.y));
+						kht_walk_erase(wk);
+					} while (kht_walk_next(wk, bits, WW));
+					rev = static_cast<unsigned int>(out - poss);
+					wk.x = xr; wk.y = y;
+					kht_walk_load(wk, bits, WW);
+					if (kht_walk_next(wk, bits, WW)) {
 						do {
-							poss[nPos++] = make_ushort2(static_cast<unsigned short>(x), static_cast<unsigned short>(yy));
-							bits[static_cast<size_t>(yy) * WW + (x >> 5)] &= ~(1u << (x & 31));
-						} while (kht_next(bits, x, yy, H, WW));
+							*out++ = make_ushort2(static_cast<unsigned short>(wk.x), static_cast<unsigned short>(wk.y));
+							kht_walk_erase(wk);
+						} while (kht_walk_next(wk, bits, WW));
 					}
+					nPos = static_cast<unsigned int>(out - poss);
 					end = nPos;
 					if (end - begin < g.minSize) { nPos = begin; end = begin; }
 					else strings[nStr++] = make_uint2(begin, end);
@@ -564,7 +601,7 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	CVB_REQUIRE(h->clusterMinSize >= 2, CVB200_E_INVALID_PARAMETER);       // 1 makes the reference's recursion endless
 	KhtGeom g;
 	memset(&g, 0, sizeof(g));
-	g.W = static_cast<int>(width); g.H = static_cast<int>(height); g.WW = static_cast<int>(div_up(width, 32));
+	g.W = static_cast<int>(width); g.H = static_cast<int>(height); g.WW = static_cast<int>(div_up(width, 32) + 1);
 	g.stride = stride; g.framePitch = framePitch;
 	// ctor + initCoords (houghkht.cxx:113-116, 501-541)
 	const float kPi = 3.1415926535897932384626433f;
@@ -588,8 +625,9 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	g.x86Simd = h->x86Simd ? 1 : 0;
 
 	// ---- phase 1: bitmap + edge counts ----
-	const size_t bitWords = static_cast<size_t>(g.H) * g.WW;
+	const size_t bitWords = static_cast<size_t>(g.H + 2) * g.WW;
 	CVB_CHECK(h->bits.ensure(batch * bitWords * 4));
+	CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream)); // the zero border rows / words the walker relies on
 	CVB_CHECK(h->edgeCount.ensure(batch * 4));
 	CVB_CHECK(h->hCounts.ensure(batch * 4));
 	CVB_CUDA(cudaMemsetAsync(h->edgeCount.p, 0, batch * 4, stream));
