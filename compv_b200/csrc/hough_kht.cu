@@ -95,7 +95,7 @@ __device__ __forceinline__ unsigned long long kht_ld64(const unsigned int* p)
 	return static_cast<unsigned long long>(p[0]) | (static_cast<unsigned long long>(p[1]) << 32);
 }
 
-__device__ __forceinline__ void kht_walk_load(KhtWalk& w, unsigned int* __restrict__ bits /* row 0 of the frame */, int WW)
+__device__ __forceinline__ void kht_walk_load(KhtWalk& w, unsigned int* bits /* row 0 of the frame */, int WW)
 {
 	const int wi = w.x >> 5;
 	const int wb = ((w.x & 31) < 16 && wi > 0) ? wi - 1 : wi; // x stays >= 16 columns away from both window edges (image borders excepted); wb + 1 <= WW - 1
@@ -115,7 +115,7 @@ __device__ __forceinline__ void kht_walk_erase(KhtWalk& w)
 }
 
 // move to the next pixel of the string; false when the current pixel has no neighbour left
-__device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* __restrict__ bits, int WW)
+__device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* bits, int WW)
 {
 	// bits x-1, x, x+1 of each row; rel == 0 only happens at the image's left border (the column left of it does not exist)
 	const int sh = w.rel - 1;
@@ -137,7 +137,7 @@ __device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* __restri
 }
 
 __global__ void __launch_bounds__(32)
-kht_link_kernel(unsigned int* __restrict__ bitsAll, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
+kht_link_kernel(unsigned int* bitsAll /* read and written through several derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
 {
 	const int frame = blockIdx.x, lane = threadIdx.x;
 	const int W = g.W, H = g.H, WW = g.WW;
