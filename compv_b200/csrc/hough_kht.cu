@@ -19,6 +19,9 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -28,7 +31,7 @@
 namespace cvb {
 
 struct KhtGeom {
-	int W, H, WW;              // WW = bitmap words per row = ceil(W/32) + 1: the last word is always zero; a frame's bitmap has H + 2 rows (a zero row above and below)
+	int W, H, WW;              // WW = bitmap words per row = ceil(W/32) + 2: one zero word before and after the pixels; a frame's bitmap has H + 2 rows (a zero row above and below)
 	size_t stride, framePitch;
 	unsigned int nRho, nTheta, cs; // cs = accumulator pitch (nRho + 2)
 	double dRho, dThetaDeg, rhoMaxNeg, halfW, halfH;
@@ -54,7 +57,7 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 	const int frame = blockIdx.z, y = blockIdx.y;
 	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned int word = 0;
-	if (wi < g.WW) {
+	if (wi < g.WW - 2) {
 		const uint8_t* row = edges + frame * g.framePitch + static_cast<size_t>(y) * g.stride;
 		const int x0 = wi * 32;
 		if (x0 + 32 <= g.W && ((reinterpret_cast<uintptr_t>(row + x0) & 15) == 0)) {
@@ -69,7 +72,7 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 		else {
 			for (int j = 0; j < 32 && x0 + j < g.W; ++j) if (row[x0 + j]) word |= 1u << j;
 		}
-		bits[(static_cast<size_t>(frame) * (g.H + 2) + y + 1) * g.WW + wi] = word;
+		bits[(static_cast<size_t>(frame) * (g.H + 2) + y + 1) * g.WW + wi + 1] = word;
 	}
 	unsigned int c = __popc(word);
 	for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -79,60 +82,61 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 // ---- linking ------------------------------------------------------------------------------------
 // The walk is a single dependent instruction chain on one lane: its cost is (instructions per step) x (issue latency, ~4 cycles).  Measured on frame G
 // (82k edge px, 5.9k walks per 1080p frame): three bitmap row loads per step 20.8 ms (~110 instr/step); shared-memory band caches 30-47 ms; a 3-row x 64-column
-// register window with bounds checks 16.0 ms (91 instr/step, ncu r1c).  This version removes the bounds checks with a zero-padded bitmap (one extra row above
-// and below, one extra word per row), keeps running pointers instead of recomputing 64-bit addresses, and picks the next pixel with one find-first-set over
-// the 8 neighbour bits in the order of Algorithm 6 (houghkht.cxx:666-703: TL, T, TR, L, R, BL, B, BR) and two packed look-up constants.
+// register window with bounds checks 16.0 ms (91 instr/step, ncu r1c); without bounds checks, running pointers 13.3 ms (~80 instr/step).  This version is written
+// for instruction count: the bitmap is zero padded on all four sides so the walker has no border case at all, the window lives in six 32-bit registers,
+// the position is one packed register (x | y << 16, the value that gets stored), the 9-bit neighbourhood is assembled in the order of Algorithm 6
+// (houghkht.cxx:666-703: TL, T, TR, L, [centre, already erased], R, BL, B, BR) so that one find-first-set yields k with dx = k % 3 - 1, dy = k / 3 - 1.
 // Every access to a frame's bitmap comes from this one warp, so its SM's L1 stays coherent with the stores.
+#define KHT_AHEAD 96
 struct KhtWalk {
-	unsigned long long t, c, b; // bitmap rows y-1, y, y+1, columns [32*wb, 32*wb + 64)
-	unsigned int* cptr;         // &row(y)[wb]
-	int rel;                    // x - 32*wb
-	int x, y;
+	unsigned int t0, t1, c0, c1, b0, b1; // bitmap rows y-1, y, y+1: padded columns [32*wb, 32*wb + 64)
+	unsigned int* p;                     // &paddedRow(y)[wb]
+	int rel;                             // padded column - 32*wb, kept in [1, 62]
+	unsigned int xy;                     // x | y << 16 (image coordinates)
 };
 
-__device__ __forceinline__ unsigned long long kht_ld64(const unsigned int* p)
+__device__ __forceinline__ void kht_walk_load(KhtWalk& w, unsigned int* bits /* padded row 0 of the frame */, int WW)
 {
-	return static_cast<unsigned long long>(p[0]) | (static_cast<unsigned long long>(p[1]) << 32);
+	const int X = static_cast<int>(w.xy & 0xffffu) + 32, y = static_cast<int>(w.xy >> 16);
+	const int wi = X >> 5; // >= 1
+	const int wb = ((X & 31) < 16) ? wi - 1 : wi; // the pixel sits in columns [16, 47] of the window; wb + 1 <= WW - 1
+	w.rel = X - (wb << 5);
+	w.p = bits + y * WW + wb;
+	w.t0 = w.p[-WW]; w.t1 = w.p[1 - WW];
+	w.c0 = w.p[0]; w.c1 = w.p[1];
+	w.b0 = w.p[WW]; w.b1 = w.p[WW + 1];
 }
 
-__device__ __forceinline__ void kht_walk_load(KhtWalk& w, unsigned int* bits /* row 0 of the frame */, int WW)
+__device__ __forceinline__ unsigned int kht_shr64(unsigned int lo, unsigned int hi, int sh) // low word of (hi:lo) >> sh, sh in [0, 63]
 {
-	const int wi = w.x >> 5;
-	const int wb = ((w.x & 31) < 16 && wi > 0) ? wi - 1 : wi; // x stays >= 16 columns away from both window edges (image borders excepted); wb + 1 <= WW - 1
-	w.rel = w.x - (wb << 5);
-	w.cptr = bits + static_cast<ptrdiff_t>(w.y) * WW + wb;
-	w.t = kht_ld64(w.cptr - WW);
-	w.c = kht_ld64(w.cptr);
-	w.b = kht_ld64(w.cptr + WW);
+	return static_cast<unsigned int>(((static_cast<unsigned long long>(hi) << 32) | lo) >> sh);
 }
 
 // erase the current pixel in the registers and in memory
 __device__ __forceinline__ void kht_walk_erase(KhtWalk& w)
 {
-	w.c &= ~(1ull << w.rel);
+	const unsigned int mask = 1u << (w.rel & 31);
 	const int hi = w.rel >> 5;
-	w.cptr[hi] = hi ? static_cast<unsigned int>(w.c >> 32) : static_cast<unsigned int>(w.c);
+	if (hi) w.c1 &= ~mask; else w.c0 &= ~mask;
+	w.p[hi] = hi ? w.c1 : w.c0;
 }
 
-// move to the next pixel of the string; false when the current pixel has no neighbour left
+// move to the next pixel of the string; false when the current (already erased) pixel has no neighbour left
 __device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* bits, int WW)
 {
-	// bits x-1, x, x+1 of each row; rel == 0 only happens at the image's left border (the column left of it does not exist)
 	const int sh = w.rel - 1;
-	const unsigned int t3 = static_cast<unsigned int>(sh >= 0 ? (w.t >> sh) : (w.t << 1)) & 7u;
-	const unsigned int c3 = static_cast<unsigned int>(sh >= 0 ? (w.c >> sh) : (w.c << 1)) & 5u;
-	const unsigned int b3 = static_cast<unsigned int>(sh >= 0 ? (w.b >> sh) : (w.b << 1)) & 7u;
-	// TL T TR L R BL B BR -> bits 0..7
-	const unsigned int m = t3 | ((c3 & 1u) << 3) | ((c3 & 4u) << 2) | (b3 << 5);
+	unsigned int m = kht_shr64(w.t0, w.t1, sh) & 7u;
+	m |= (kht_shr64(w.c0, w.c1, sh) & 7u) << 3;
+	m |= (kht_shr64(w.b0, w.b1, sh) & 7u) << 6;
 	if (!m) return false;
-	const int k2 = (__ffs(m) - 1) << 1;
-	const int dx = static_cast<int>((0x9224u >> k2) & 3u) - 1;  // dx + 1 for k = 0..7: 0 1 2 0 2 0 1 2
-	const int dy = static_cast<int>((0xa940u >> k2) & 3u) - 1;  // dy + 1 for k = 0..7: 0 0 0 1 1 2 2 2
-	w.x += dx; w.y += dy; w.rel += dx;
-	// leaving the window horizontally: only possible away from the image borders (wb > 0 on the left, more words on the right)
-	if ((w.rel < 1 && w.x > 0) || (w.rel > 62 && (w.x >> 5) + 1 < WW - 1)) { kht_walk_load(w, bits, WW); return true; }
-	if (dy < 0) { w.cptr -= WW; w.b = w.c; w.c = w.t; w.t = kht_ld64(w.cptr - WW); }
-	else if (dy > 0) { w.cptr += WW; w.t = w.c; w.c = w.b; w.b = kht_ld64(w.cptr + WW); }
+	const int k = __ffs(m) - 1;           // 0..8 (never 4: the centre is erased)
+	const int dy1 = (k * 11) >> 5;        // k / 3
+	const int dx1 = k - 3 * dy1;          // k % 3
+	w.rel += dx1 - 1;
+	w.xy += static_cast<unsigned int>(dx1 + (dy1 << 16) - 65537);
+	if (static_cast<unsigned int>(w.rel - 1) > 61u) { kht_walk_load(w, bits, WW); return true; } // left the window sideways: re-centre
+	if (dy1 == 0) { w.p -= WW; w.b0 = w.c0; w.b1 = w.c1; w.c0 = w.t0; w.c1 = w.t1; w.t0 = w.p[-WW]; w.t1 = w.p[1 - WW]; }
+	else if (dy1 == 2) { w.p += WW; w.t0 = w.c0; w.t1 = w.c1; w.c0 = w.b0; w.c1 = w.b1; w.b0 = w.p[WW]; w.b1 = w.p[WW + 1]; }
 	return true;
 }
 
@@ -141,19 +145,29 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through several derive
 {
 	const int frame = blockIdx.x, lane = threadIdx.x;
 	const int W = g.W, H = g.H, WW = g.WW;
-	unsigned int* bits = bitsAll + (static_cast<size_t>(frame) * (H + 2) + 1) * WW; // row 0 of the frame (row -1 and row H are zero)
+	unsigned int* bits = bitsAll + (static_cast<size_t>(frame) * (H + 2) + 1) * WW; // padded row 0 of the frame
 	KhtFrame& fr = frames[frame];
-	ushort2* poss = possAll + fr.posOff;
+	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff); // ushort2 {x, y} written as x | y << 16
 	uint2* strings = stringsAll + fr.strOff;
 	unsigned int nPos = 0, nStr = 0; // meaningful on lane 0
 	const int lastWord = (W - 1) >> 5;
 
+	// The seed scan reads rows in order, so rows above the scan line are in this SM's L1; walks mostly head DOWN into rows nobody has read yet and
+	// would pay an L2 round trip per new row (the chain's dominant latency).  The idle lanes therefore keep KHT_AHEAD rows below the scan line prefetched.
+	const char* bytes0 = reinterpret_cast<const char*>(bits - WW);                       // padded row -1
+	const size_t bytesEnd = static_cast<size_t>(H + 2) * WW * 4;
+	for (size_t o = static_cast<size_t>(lane) * 128; o < bytesEnd && o < static_cast<size_t>(KHT_AHEAD + 2) * WW * 4; o += 32 * 128)
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
 	for (int y = 1; y < H - 1; ++y) {
-		unsigned int* row = bits + static_cast<size_t>(y) * WW;
+		const unsigned int* row = bits + static_cast<size_t>(y) * WW + 1; // word 0 of the image row
+		{
+			const size_t o = static_cast<size_t>(y + 1 + KHT_AHEAD) * WW * 4 + static_cast<size_t>(lane) * 128; // row y + KHT_AHEAD, one 128-byte line per lane
+			if (o < bytesEnd && lane * 128 < WW * 4 + 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
+		}
 		for (int wb = 0; wb <= lastWord; wb += 32) {
 			while (true) {
 				const int wi = wb + lane;
-				unsigned int w = (wi <= lastWord) ? row[wi] : 0u;
+				unsigned int w = (wi <= lastWord) ? row[wi] : 0u; // plain load: served by this SM's L1, which the walker's stores keep current
 				// seeds are interior columns only: x in [1, W-2]
 				if (wi == 0) w &= ~1u;
 				if (wi == lastWord) w &= ~(1u << ((W - 1) & 31));
@@ -166,20 +180,20 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through several derive
 				if (lane == 0) {
 					// Algorithm 5 (houghkht.cxx:706-760)
 					begin = nPos;
-					ushort2* out = poss + nPos;
+					unsigned int* out = poss + nPos;
 					KhtWalk wk;
-					wk.x = xr; wk.y = y;
+					wk.xy = static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16);
 					kht_walk_load(wk, bits, WW);
 					do {
-						*out++ = make_ushort2(static_cast<unsigned short>(wk.x), static_cast<unsigned short>(wk.y));
+						*out++ = wk.xy;
 						kht_walk_erase(wk);
 					} while (kht_walk_next(wk, bits, WW));
 					rev = static_cast<unsigned int>(out - poss);
-					wk.x = xr; wk.y = y;
+					wk.xy = static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16);
 					kht_walk_load(wk, bits, WW);
 					if (kht_walk_next(wk, bits, WW)) {
 						do {
-							*out++ = make_ushort2(static_cast<unsigned short>(wk.x), static_cast<unsigned short>(wk.y));
+							*out++ = wk.xy;
 							kht_walk_erase(wk);
 						} while (kht_walk_next(wk, bits, WW));
 					}
@@ -195,7 +209,7 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through several derive
 				if (end > begin) { // the first walk is stored reversed (std::reverse, houghkht.cxx:752-755)
 					const unsigned int n = rev - begin;
 					for (unsigned int i = lane; i < n / 2; i += 32) {
-						const ushort2 a = poss[begin + i], b = poss[begin + n - 1 - i];
+						const unsigned int a = poss[begin + i], b = poss[begin + n - 1 - i];
 						poss[begin + i] = b; poss[begin + n - 1 - i] = a;
 					}
 				}
@@ -597,11 +611,12 @@ using namespace cvb;
 int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
 	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream)
 {
+	const auto tCall0 = std::chrono::steady_clock::now();
 	CVB_REQUIRE(width <= 65535 && height <= 65535, CVB200_E_OUT_OF_BOUND); // positions are stored as 16-bit coordinates
 	CVB_REQUIRE(h->clusterMinSize >= 2, CVB200_E_INVALID_PARAMETER);       // 1 makes the reference's recursion endless
 	KhtGeom g;
 	memset(&g, 0, sizeof(g));
-	g.W = static_cast<int>(width); g.H = static_cast<int>(height); g.WW = static_cast<int>(div_up(width, 32) + 1);
+	g.W = static_cast<int>(width); g.H = static_cast<int>(height); g.WW = static_cast<int>(div_up(width, 32) + 2);
 	g.stride = stride; g.framePitch = framePitch;
 	// ctor + initCoords (houghkht.cxx:113-116, 501-541)
 	const float kPi = 3.1415926535897932384626433f;
@@ -707,10 +722,13 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	CVB_CUDA(cudaStreamSynchronize(stream));
 	for (size_t f = 0; f < batch; ++f) CVB_REQUIRE(hf[f].nVotes <= votesCap, CVB200_E_OUT_OF_BOUND);
 	KhtVote* hv = h->hVotes.as<KhtVote>();
-	for (size_t f = 0; f < batch; ++f) {
-		if (hf[f].nVotes) CVB_CUDA(cudaMemcpyAsync(hv + f * votesCap, h->votes.as<KhtVote>() + f * votesCap, hf[f].nVotes * sizeof(KhtVote), cudaMemcpyDeviceToHost, stream));
+	{
+		size_t maxVotes = 0; // one strided copy for the whole batch: the leading maxVotes cells of every frame's list
+		for (size_t f = 0; f < batch; ++f) maxVotes = std::max<size_t>(maxVotes, hf[f].nVotes);
+		if (maxVotes) CVB_CUDA(cudaMemcpy2DAsync(hv, votesCap * sizeof(KhtVote), h->votes.p, votesCap * sizeof(KhtVote), maxVotes * sizeof(KhtVote), batch, cudaMemcpyDeviceToHost, stream));
 	}
 	CVB_CUDA(cudaStreamSynchronize(stream));
+	const auto tHost0 = std::chrono::steady_clock::now();
 
 	// ---- host: sort + sweep (houghkht.cxx:1195-1247). std::sort of the same libstdc++ on the same input order = the reference's tie order ----
 	// Frames are independent: a few host threads share them (the sort of a few thousand cells per frame is the only per-frame host work).
@@ -745,7 +763,7 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	};
 	{
 		size_t nThreads = std::thread::hardware_concurrency();
-		if (nThreads > 16) nThreads = 16;
+		if (nThreads > 64) nThreads = 64;
 		if (nThreads > batch) nThreads = batch;
 		if (nThreads <= 1) finishFrames(0, batch);
 		else {
@@ -761,6 +779,12 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	{
 		const size_t f = batch - 1;
 		h->lastGs = (hf[f].nStr && hf[f].nClus) ? hf[f].gs : 1.0;
+	}
+	if (getenv("CVB200_TRACE")) {
+		const auto t1 = std::chrono::steady_clock::now();
+		size_t nv = 0; for (size_t f = 0; f < batch; ++f) nv += hf[f].nVotes;
+		fprintf(stderr, "[cvb200] kht batch %zu: device+copies %.3f ms, host peaks %.3f ms (%zu cells)\n", batch,
+			std::chrono::duration<double, std::milli>(tHost0 - tCall0).count(), std::chrono::duration<double, std::milli>(t1 - tHost0).count(), nv);
 	}
 	return CVB200_S_OK;
 }

@@ -130,11 +130,175 @@ def row_mser(args):
     emit("a12", batch, ms, extra)
 
 
-ROWS = {"sht": row_sht, "lsl": row_lsl, "mser": row_mser}
+PEAK_GBS = None
+
+
+def hbm_peak():
+    global PEAK_GBS
+    if PEAK_GBS is None:
+        try:
+            PEAK_GBS = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            PEAK_GBS = 6574.5
+    return PEAK_GBS
+
+
+def g_frames(batch):
+    frames = np.stack([frame_g(W, H, 12345 + k) for k in range(min(batch, 8))])
+    d_in = torch.from_numpy(frames).cuda()
+    return frames, d_in.repeat((batch + len(frames) - 1) // len(frames), 1, 1)[:batch].contiguous()
+
+
+def simple_row(args, row, workload, alg_bytes_per_px, step, ref_ms=None, extra=None):
+    """alg_bytes_per_px: SURVEY section 8(d)'s algorithmic bytes; achieved GB/s = bytes / time of the whole call (all its kernels)."""
+    ms = timed(step, args.steps)
+    px = args.batch * W * H
+    gbs = alg_bytes_per_px * px / (ms * 1e-3) / 1e9
+    d = {"workload": workload, "alg_bytes_per_px": alg_bytes_per_px, "achieved_GBps": round(gbs, 1), "hbm_peak_GBps": hbm_peak(), "frac_of_hbm_peak": round(gbs / hbm_peak(), 4),
+         "kernels_ms": kernel_split(step, args.steps)}
+    if ref_ms is not None:
+        d["cpu_reference_ms_per_frame"] = round(float(ref_ms), 3)
+    if extra:
+        d.update(extra)
+    emit(row, args.batch, ms, d)
+
+
+def row_convlt(args):
+    import oracle
+    frames, d_in = g_frames(args.batch)
+    stream = torch.cuda.current_stream().cuda_stream
+    k = cvb.gauss_kernel(5, 1.0)
+    d_out8 = torch.empty_like(d_in)
+    lib = cvb.lib()
+
+    def step8():
+        cvb.check(lib.cvb200_convlt1_8u32f8u_dev(_ffi.vp(d_in), _ffi.sz(W), _ffi.sz(H), _ffi.sz(W), _ffi.vp(k), _ffi.vp(k), _ffi.sz(5), _ffi.vp(d_out8), 0, _ffi.sz(args.batch), _ffi.sz(0), C.c_void_p(stream)), "convlt")
+    ref = None
+    if oracle.have_ref():
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            oracle.convlt1("ref", "8u32f8u", frames[0], k, k)
+            t.append((time.perf_counter() - t0) * 1e3)
+        ref = min(t)
+    simple_row(args, "a2", "convlt1<u8,f32,u8> 5-tap Gaussian (sigma 1), 1080p", 2, step8, ref)
+    sob = np.array([-1, 0, 1], np.int16)
+    smooth = np.array([1, 2, 1], np.int16)
+    d_out16 = torch.empty((args.batch, H, W), dtype=torch.int16, device="cuda")
+
+    def step16():
+        cvb.check(lib.cvb200_convlt1_8u16s16s_dev(_ffi.vp(d_in), _ffi.sz(W), _ffi.sz(H), _ffi.sz(W), _ffi.vp(smooth), _ffi.vp(sob), _ffi.sz(3), _ffi.vp(d_out16), 0, _ffi.sz(args.batch), _ffi.sz(0), C.c_void_p(stream)), "convlt")
+    simple_row(args, "a2", "convlt1<u8,i16,i16> 3-tap Sobel gx, 1080p", 3, step16)
+
+
+def row_sobel(args):
+    import oracle
+    frames, d_in = g_frames(args.batch)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_out = torch.empty_like(d_in)
+    sob = cvb.CompVEdgeDete.newObj(_ffi.SOBEL_ID)
+
+    def step():
+        sob.process_dev(d_in, W, H, W, d_out, batch=args.batch, stream=stream)
+    ref = float(np.median(oracle.time_edge_dete(frames[0], kind="sobel", iters=5, threads=-1))) if oracle.have_ref() else None
+    simple_row(args, "a3", "Sobel edge detector (gx, gy, L1 magnitude, frame max, normalise), 1080p", 2, step, ref)
+    canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
+    canny.set_preblur(5, 1.0)
+
+    def stepc():
+        canny.process_dev(d_in, W, H, W, d_out, batch=args.batch, stream=stream)
+    refc = float(np.median(oracle.time_edge_dete(frames[0], kind="canny", tlow=59.0, thigh=119.0, blur_size=5, blur_sigma=1.0, iters=5, threads=-1))) if oracle.have_ref() else None
+    simple_row(args, "a5", "Gaussian 5x5 + Canny 59/119, 1080p (frame G)", 2, stepc, refc)
+
+
+def row_gradient(args):
+    frames, d_in = g_frames(args.batch)
+    stream = torch.cuda.current_stream().cuda_stream
+    mag = torch.empty((args.batch, H, W), dtype=torch.float32, device="cuda")
+    dire = torch.empty_like(mag)
+    lib = cvb.lib()
+
+    def step():
+        cvb.check(lib.cvb200_gradient_fast_8u_dev(_ffi.vp(d_in), _ffi.sz(W), _ffi.sz(H), _ffi.sz(W), None, None, None, None, _ffi.vp(mag), _ffi.vp(dire), _ffi.sz(args.batch), _ffi.sz(0), C.c_void_p(stream)), "gradient")
+    simple_row(args, "a4", "CompVGradientFast magnitude + direction (f32 out), 1080p", 9, step)
+
+
+def row_fast(args):
+    import oracle
+    frames, d_in = g_frames(args.batch)
+    stream = torch.cuda.current_stream().cuda_stream
+    cap = 8192
+    d_pts = torch.empty((args.batch, cap, 6), dtype=torch.float32, device="cuda")
+    d_cnt = torch.zeros(args.batch, dtype=torch.int32, device="cuda")
+    fast = cvb.CompVCornerDete.newObj(_ffi.FAST_ID)
+    fast.setInt(_ffi.FAST_SET_INT_THRESHOLD, 20)
+    fast.setBool(_ffi.FAST_SET_BOOL_NON_MAXIMA_SUPP, True)
+
+    def step():
+        fast.process_dev(d_in, W, H, W, d_pts, cap, d_cnt, batch=args.batch, stream=stream)
+    ref = None
+    if oracle.have_ref():
+        _, t = oracle.fast_detect("ref", frames[0], 9, 20, True, threads=-1, iters=5)
+        ref = float(np.median(t))
+    step()
+    torch.cuda.synchronize()
+    simple_row(args, "a8", "FAST9 threshold 20 + NMS, 1080p (frame G)", 1, step, ref, {"corners_frame0": int(d_cnt[0].item())})
+
+
+def row_hog(args):
+    import oracle
+    frames, d_in = g_frames(args.batch)
+    stream = torch.cuda.current_stream().cuda_stream
+    hog = cvb.CompVHOG.newObj()
+    n = hog.descriptorSize(W, H)
+    d_out = torch.empty((args.batch, n), dtype=torch.float32, device="cuda")
+
+    def step():
+        hog.process_dev(d_in, W, H, W, d_out, batch=args.batch, stream=stream)
+    ref = None
+    if oracle.have_ref():
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            oracle.hog("ref", frames[0], threads=-1)
+            t.append((time.perf_counter() - t0) * 1e3)
+        ref = min(t)
+    simple_row(args, "a9", "S-HOG 8x8 cells, 16x16 blocks, stride 8, 9 bins, L2Hys, bilinear; 1080p as one window", 3.25, step, ref, {"descriptor_floats": int(n)})
+
+
+def row_threshold(args):
+    import oracle
+    frames, d_in = g_frames(args.batch)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_out = torch.empty_like(d_in)
+    d_thr = torch.zeros(args.batch, dtype=torch.float64, device="cuda")
+    d_hist = torch.zeros(args.batch * 256, dtype=torch.int32, device="cuda")
+    lib = cvb.lib()
+
+    def otsu():
+        cvb.check(lib.cvb200_threshold_otsu_dev(_ffi.vp(d_in), _ffi.sz(W), _ffi.sz(H), _ffi.sz(W), _ffi.vp(d_thr), _ffi.vp(d_out), _ffi.vp(d_hist), _ffi.sz(args.batch), _ffi.sz(0), C.c_void_p(stream)), "otsu")
+
+    def adaptive():
+        cvb.check(lib.cvb200_threshold_adaptive_dev(_ffi.vp(d_in), _ffi.sz(W), _ffi.sz(H), _ffi.sz(W), _ffi.sz(5), C.c_double(8.0), C.c_double(255.0), 0, _ffi.vp(d_out), _ffi.sz(args.batch), _ffi.sz(0), C.c_void_p(stream)), "adaptive")
+    r1 = r2 = None
+    if oracle.have_ref():
+        def tm(mode):
+            t = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                oracle.threshold("ref", mode, frames[0], threads=-1)
+                t.append((time.perf_counter() - t0) * 1e3)
+            return min(t)
+        r1, r2 = tm("otsu"), tm("adaptive")
+    simple_row(args, "a10", "Otsu threshold (histogram + threshold + binarise), 1080p", 3, otsu, r1)
+    simple_row(args, "a10", "adaptive threshold, 5x5 fixed-point mean, delta 8, 1080p", 2, adaptive, r2)
+
+
+ROWS = {"convlt": row_convlt, "sobel": row_sobel, "gradient": row_gradient, "fast": row_fast, "hog": row_hog, "threshold": row_threshold, "sht": row_sht, "lsl": row_lsl, "mser": row_mser}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", default="sht,lsl,mser")
+    ap.add_argument("--rows", default="convlt,sobel,gradient,fast,hog,threshold,sht,lsl,mser")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
