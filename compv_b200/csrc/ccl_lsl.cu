@@ -170,53 +170,75 @@ __global__ void __launch_bounds__(64) lsl_emit_kernel(const unsigned int* __rest
 }
 
 // ---- step 2.1: one warp per frame, raster order ----
-__global__ void __launch_bounds__(32) lsl_equiv_kernel(const ushort2* __restrict__ ov, int* __restrict__ label, int* __restrict__ eqAll, LslFrame* __restrict__ frames, LslGeom g)
+// The reference visits the segments one by one (:441-473).  Three kinds: NEW (touches no previous-row segment: takes the next label), SIMPLE (touches exactly
+// one: copies EQ[label of that segment]) and MERGING (touches several: reads and rewrites EQ).  Only MERGING segments change what later segments read, and NEW
+// ones only append to EQ, so a run of consecutive NEW / SIMPLE segments of one row gives the same result processed all at once: 32 segments are fetched, the
+// warp walks the runs between "barriers" (a MERGING segment, handled by its own lane alone, or the first segment of a row, where the label rings swap).
+__device__ __forceinline__ int lsl_eq_get(const int* eqS, const int* eqG, int eqCap, int ea) { return (ea < eqCap) ? eqS[ea] : eqG[ea]; }
+__device__ __forceinline__ void lsl_eq_set(int* eqS, int* eqG, int eqCap, int ea, int v) { if (ea < eqCap) eqS[ea] = v; else eqG[ea] = v; }
+
+__global__ void __launch_bounds__(32) lsl_equiv_kernel(const ushort2* __restrict__ ov, int* __restrict__ label, int* eqAll, LslFrame* frames, LslGeom g)
 {
 	extern __shared__ int sm[];
-	int* ringA = sm;
-	int* ringB = sm + g.ringCap;
+	int* prev = sm;
+	int* cur = sm + g.ringCap;
 	int* eqS = sm + 2 * g.ringCap;
 	const int f = blockIdx.x, lane = threadIdx.x;
 	const unsigned int base = frames[f].segBase, nseg = frames[f].nseg;
 	int* eqG = eqAll + base + f; // nseg + 1 entries per frame
 	const int eqCap = g.eqCap;
-	int* prev = ringA; int* cur = ringB;
-	int curN = 0, nea = 0;
+	const unsigned int ltMask = (1u << lane) - 1u;
+	int curN = 0, nea = 0; // uniform across the warp
 	for (unsigned int s0 = 0; s0 < nseg; s0 += 32) {
-		const unsigned int cnt = min(32u, nseg - s0);
+		const int cnt = static_cast<int>(min(32u, nseg - s0));
+		const bool valid = lane < cnt;
 		ushort2 mine = make_ushort2(0, 0);
-		if (lane < cnt) mine = ov[base + s0 + lane];
-		const unsigned int packed = static_cast<unsigned int>(mine.x) | (static_cast<unsigned int>(mine.y) << 16);
-		int myLabel = 0;
-		for (unsigned int t = 0; t < cnt; ++t) {
-			const unsigned int v = __shfl_sync(0xffffffffu, packed, t);
-			int lab = 0;
-			if (lane == 0) {
-				const int k0 = v & 0x7fff, k1p = v >> 16;
-				if (v & 0x8000u) { int* tmp = prev; prev = cur; cur = tmp; curN = 0; }
-				if (k1p > k0) { // :449-465
+		if (valid) mine = ov[base + s0 + lane];
+		const int k0 = mine.x & 0x7fff, k1p = mine.y;
+		const int n = k1p - k0;                                  // previous-row segments touched
+		const unsigned int fMask = __ballot_sync(0xffffffffu, valid && (mine.x & 0x8000u)); // first segment of a row
+		const unsigned int cMask = __ballot_sync(0xffffffffu, valid && n >= 2);             // merging segments
+		int lab = 0;
+		int pos = 0;
+		while (pos < cnt) {
+			if ((fMask >> pos) & 1u) { int* tmp = prev; prev = cur; cur = tmp; curN = 0; }
+			if ((cMask >> pos) & 1u) {
+				if (lane == pos) { // :449-465, alone
 					int ea = prev[k0];
-					int a = (ea < eqCap) ? eqS[ea] : eqG[ea];
+					int a = lsl_eq_get(eqS, eqG, eqCap, ea);
 					for (int kk = k0 + 1; kk < k1p; ++kk) {
 						const int eak = prev[kk];
-						const int ak = (eak < eqCap) ? eqS[eak] : eqG[eak];
-						if (a < ak) { if (eak < eqCap) eqS[eak] = a; else eqG[eak] = a; }
-						else { a = ak; if (ea < eqCap) eqS[ea] = a; else eqG[ea] = a; ea = eak; }
+						const int ak = lsl_eq_get(eqS, eqG, eqCap, eak);
+						if (a < ak) lsl_eq_set(eqS, eqG, eqCap, eak, a);
+						else { a = ak; lsl_eq_set(eqS, eqG, eqCap, ea, a); ea = eak; }
 					}
 					lab = a;
+					cur[curN] = a;
 				}
-				else { // :467-469 new label; EQ[ea] = ea is written when the label is born instead of pre-filling the table (build_EQ :531-541)
-					lab = ++nea;
-					if (lab < eqCap) eqS[lab] = lab; else eqG[lab] = lab;
-				}
-				cur[curN++] = lab;
+				__syncwarp();
+				++curN; ++pos;
+				continue;
 			}
-			lab = __shfl_sync(0xffffffffu, lab, 0);
-			if (lane == t) myLabel = lab;
+			// run of NEW / SIMPLE segments [pos, next): up to the next barrier
+			const unsigned int later = (fMask | cMask) & ~((2u << pos) - 1u);
+			const int next = later ? min(cnt, __ffs(later) - 1) : cnt;
+			const bool mineNow = (lane >= pos) && (lane < next);
+			const unsigned int newMask = __ballot_sync(0xffffffffu, mineNow && n <= 0);
+			if (mineNow) {
+				if (n <= 0) { // :467-469; EQ[ea] = ea is written when the label is born instead of pre-filling the table (build_EQ :531-541)
+					lab = nea + __popc(newMask & ltMask) + 1;
+					lsl_eq_set(eqS, eqG, eqCap, lab, lab);
+				}
+				else lab = lsl_eq_get(eqS, eqG, eqCap, prev[k0]); // :449-451 with an empty loop, :466
+				cur[curN + lane - pos] = lab;
+			}
+			__syncwarp();
+			nea += __popc(newMask);
+			curN += next - pos;
+			pos = next;
 		}
-		if (lane < cnt) label[base + s0 + lane] = myLabel;
+		if (valid) label[base + s0 + lane] = lab;
 	}
-	nea = __shfl_sync(0xffffffffu, nea, 0);
 	__syncwarp();
 	for (int ea = 1 + lane; ea <= nea && ea < eqCap; ea += 32) eqG[ea] = eqS[ea];
 	if (lane == 0) { eqG[0] = 0; frames[f].nea = nea; }

@@ -200,14 +200,14 @@ def row_sobel(args):
 
     def step():
         sob.process_dev(d_in, W, H, W, d_out, batch=args.batch, stream=stream)
-    ref = float(np.median(oracle.time_edge_dete(frames[0], kind="sobel", iters=5, threads=-1))) if oracle.have_ref() else None
+    ref = float(np.median(oracle.time_edge_dete(frames[0], kind="sobel", iters=5, threads=-1)[0])) if oracle.have_ref() else None
     simple_row(args, "a3", "Sobel edge detector (gx, gy, L1 magnitude, frame max, normalise), 1080p", 2, step, ref)
     canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
     canny.set_preblur(5, 1.0)
 
     def stepc():
         canny.process_dev(d_in, W, H, W, d_out, batch=args.batch, stream=stream)
-    refc = float(np.median(oracle.time_edge_dete(frames[0], kind="canny", tlow=59.0, thigh=119.0, blur_size=5, blur_sigma=1.0, iters=5, threads=-1))) if oracle.have_ref() else None
+    refc = float(np.median(oracle.time_edge_dete(frames[0], kind="canny", tlow=59.0, thigh=119.0, blur_size=5, blur_sigma=1.0, iters=5, threads=-1)[0])) if oracle.have_ref() else None
     simple_row(args, "a5", "Gaussian 5x5 + Canny 59/119, 1080p (frame G)", 2, stepc, refc)
 
 
