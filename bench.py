@@ -154,6 +154,7 @@ def main():
     cvb.init(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     B = args.frames
