@@ -31,6 +31,7 @@ struct LslGeom {
 	int ringCap;               // label ring capacity = max segments per row
 };
 struct LslFrame { unsigned int segBase, nseg; int nea, na; };
+#define LSL_STAGE 1024
 
 __device__ __forceinline__ unsigned int lsl_pack4(unsigned int v) // bit 0 of each of 4 bytes -> 4-bit nibble
 {
@@ -189,11 +190,24 @@ __global__ void __launch_bounds__(32) lsl_equiv_kernel(const ushort2* __restrict
 	const int eqCap = g.eqCap;
 	const unsigned int ltMask = (1u << lane) - 1u;
 	int curN = 0, nea = 0; // uniform across the warp
+	// The descriptors were written by another kernel: every fetch is an L2 round trip.  They are staged 1024 at a time (32 independent loads per lane in flight)
+	// so that the round trip is paid once per 1024 segments instead of once per group of 32.
+	unsigned int* ovS = reinterpret_cast<unsigned int*>(sm + 2 * g.ringCap + g.eqCap); // LSL_STAGE entries
+	const unsigned int* ov32 = reinterpret_cast<const unsigned int*>(ov + base);
 	for (unsigned int s0 = 0; s0 < nseg; s0 += 32) {
+		if ((s0 & (LSL_STAGE - 1)) == 0) {
+			__syncwarp();
+			#pragma unroll 8
+			for (int i = 0; i < LSL_STAGE / 32; ++i) {
+				const unsigned int k = s0 + i * 32 + lane;
+				if (k < nseg) ovS[i * 32 + lane] = ov32[k];
+			}
+			__syncwarp();
+		}
 		const int cnt = static_cast<int>(min(32u, nseg - s0));
 		const bool valid = lane < cnt;
 		ushort2 mine = make_ushort2(0, 0);
-		if (valid) mine = ov[base + s0 + lane];
+		if (valid) { const unsigned int v = ovS[(s0 & (LSL_STAGE - 1)) + lane]; mine.x = static_cast<unsigned short>(v & 0xffffu); mine.y = static_cast<unsigned short>(v >> 16); }
 		const int k0 = mine.x & 0x7fff, k1p = mine.y;
 		const int n = k1p - k0;                                  // previous-row segments touched
 		const unsigned int fMask = __ballot_sync(0xffffffffu, valid && (mine.x & 0x8000u)); // first segment of a row
@@ -339,7 +353,7 @@ static int lsl_process_dev(cvb200_ccl* c, const uint8_t* binar, size_t width, si
 	g.ringCap = static_cast<int>((width + 1) / 2 + 1);
 	g.eqCap = 20480; // 80 KB of EQ per frame-warp: two frames per SM; labels beyond it live in global memory
 	const size_t smemMax = 200 * 1024;
-	if ((static_cast<size_t>(g.ringCap) * 2 + g.eqCap) * 4 > smemMax) g.eqCap = static_cast<int>(smemMax / 4 - static_cast<size_t>(g.ringCap) * 2);
+	if ((static_cast<size_t>(g.ringCap) * 2 + g.eqCap + LSL_STAGE) * 4 > smemMax) g.eqCap = static_cast<int>(smemMax / 4 - static_cast<size_t>(g.ringCap) * 2 - LSL_STAGE);
 	const size_t words = static_cast<size_t>(g.H) * g.WW;
 	CVB_CHECK(c->fg.ensure(batch * words * 4));
 	CVB_CHECK(c->spre.ensure(batch * words * 2));
@@ -386,7 +400,7 @@ static int lsl_process_dev(cvb200_ccl* c, const uint8_t* binar, size_t width, si
 		}
 		CVB_LAUNCHED();
 		{
-			const size_t smem = (static_cast<size_t>(g.ringCap) * 2 + g.eqCap) * 4;
+			const size_t smem = (static_cast<size_t>(g.ringCap) * 2 + g.eqCap + LSL_STAGE) * 4;
 			CVB_CUDA(cudaFuncSetAttribute(lsl_equiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 			KernelScope ks_("lsl_equiv", stream);
 			lsl_equiv_kernel<<<B, 32, smem, stream>>>(c->ov.as<ushort2>(), c->label.as<int>(), c->eq.as<int>(), dFrames, g);

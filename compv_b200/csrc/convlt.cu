@@ -33,16 +33,20 @@ struct Taps {
 //               which GCC contracts to sum = fma(v, c, sum) in tap order starting from 0 (reproduces the reference's md5_fma goldens,
 //               unittests/math_convlt.cxx:17-26); conversion to u8 truncates (cvttps) and saturates.
 // fixed point  : compv_math_convlt.h:386-405 (sum of (v*k)>>16, clip 0..255)
-template <typename In, typename K, typename Out, bool FXP>
-__device__ __forceinline__ Out conv_sample(const In* p, int step, const K* taps, int ks)
+// KS > 0: the kernel size is a compile-time constant (loops unroll, taps live in registers); KS == 0: any odd size up to CONV_MAX_TAPS.
+template <typename In, typename K, typename Out, bool FXP, int KS>
+__device__ __forceinline__ Out conv_sample(const In* p, int step, const K* taps, int ksRuntime)
 {
+	const int ks = KS > 0 ? KS : ksRuntime;
 	if constexpr (FXP) {
 		unsigned int sum = 0;
+		#pragma unroll
 		for (int k = 0; k < ks; ++k) sum += (static_cast<unsigned int>(p[k * step]) * static_cast<unsigned int>(taps[k])) >> 16;
 		return static_cast<Out>(sum > 255u ? 255u : sum);
 	}
 	else if constexpr (std::is_floating_point<K>::value) {
 		float sum = 0.f;
+		#pragma unroll
 		for (int k = 0; k < ks; ++k) sum = __fmaf_rn(static_cast<float>(p[k * step]), taps[k], sum);
 		if constexpr (std::is_same<Out, uint8_t>::value) {
 			sum = fminf(fmaxf(sum, 0.f), 255.f);
@@ -54,6 +58,7 @@ __device__ __forceinline__ Out conv_sample(const In* p, int step, const K* taps,
 	}
 	else {
 		int sum = 0;
+		#pragma unroll
 		for (int k = 0; k < ks; ++k) sum += static_cast<int>(p[k * step]) * static_cast<int>(taps[k]);
 		constexpr int lo = std::is_signed<Out>::value ? -(1 << (8 * sizeof(Out) - 1)) : 0;
 		constexpr int hi = std::is_signed<Out>::value ? (1 << (8 * sizeof(Out) - 1)) - 1 : (1 << (8 * sizeof(Out))) - 1;
@@ -61,12 +66,20 @@ __device__ __forceinline__ Out conv_sample(const In* p, int step, const K* taps,
 	}
 }
 
-template <typename In, typename K, typename Out, bool FXP>
+template <typename In, typename K, typename Out, bool FXP, int KS>
 __global__ void __launch_bounds__(CONV_THREADS)
-convlt1_kernel(const In* __restrict__ in, Out* __restrict__ out, int W, int H, size_t stride, size_t framePitch, const Taps<K> taps, int ks, int border)
+convlt1_kernel(const In* __restrict__ in, Out* __restrict__ out, int W, int H, size_t stride, size_t framePitch, const Taps<K> taps, int ksRuntime, int border)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int ks = KS > 0 ? KS : ksRuntime;
 	const int r = ks >> 1;
+	K hz[KS > 0 ? KS : 1], vt[KS > 0 ? KS : 1]; // register copies of the taps when the size is known
+	if (KS > 0) {
+		#pragma unroll
+		for (int k = 0; k < KS; ++k) { hz[k] = taps.hz[k]; vt[k] = taps.vt[k]; }
+	}
+	const K* hzTaps = KS > 0 ? hz : taps.hz;
+	const K* vtTaps = KS > 0 ? vt : taps.vt;
 	const int tw = CONV_TW + 2 * r, th = CONV_TH + 2 * r;
 	In* sIn = reinterpret_cast<In*>(smem_raw);
 	const size_t inBytes = (static_cast<size_t>(tw) * th * sizeof(In) + 15) & ~static_cast<size_t>(15);
@@ -77,13 +90,17 @@ convlt1_kernel(const In* __restrict__ in, Out* __restrict__ out, int W, int H, s
 	out += blockIdx.z * framePitch;
 	const int tid = threadIdx.x;
 
-	// stage the input tile (+halo); samples outside the image are never used by a valid output, store 0
-	for (int i = tid; i < tw * th; i += CONV_THREADS) {
-		const int ly = i / tw, lx = i - ly * tw;
-		const int gx = x0 - r + lx, gy = y0 - r + ly;
-		In v = 0;
-		if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = in[static_cast<size_t>(gy) * stride + gx];
-		sIn[i] = v;
+	// stage the input tile (+halo), one warp per tile row; samples outside the image are never used by a valid output, store 0
+	for (int ly = tid >> 5; ly < th; ly += CONV_THREADS / 32) {
+		const int gy = y0 - r + ly;
+		const bool rowIn = (gy >= 0 && gy < H);
+		const In* src = in + static_cast<size_t>(rowIn ? gy : 0) * stride;
+		for (int lx = tid & 31; lx < tw; lx += 32) {
+			const int gx = x0 - r + lx;
+			In v = 0;
+			if (rowIn && gx >= 0 && gx < W) v = src[gx];
+			sIn[ly * tw + lx] = v;
+		}
 	}
 	__syncthreads();
 
@@ -94,7 +111,7 @@ convlt1_kernel(const In* __restrict__ in, Out* __restrict__ out, int W, int H, s
 		Out m = 0;
 		if (gy >= 0 && gy < H && gx < W) {
 			if (gx >= r && gx < W - r) {
-				m = conv_sample<In, K, Out, FXP>(&sIn[ly * tw + lx], 1, taps.hz, ks);
+				m = conv_sample<In, K, Out, FXP, KS>(&sIn[ly * tw + lx], 1, hzTaps, ks);
 			}
 			else if (border == CVB200_BORDER_TYPE_REPLICATE) {
 				m = static_cast<Out>(sIn[ly * tw + lx + r]);
@@ -112,7 +129,7 @@ convlt1_kernel(const In* __restrict__ in, Out* __restrict__ out, int W, int H, s
 		Out* o = &out[static_cast<size_t>(gy) * stride + gx];
 		if (gy >= r && gy < H - r) {
 			if (border == CVB200_BORDER_TYPE_IGNORE && (gx < r || gx >= W - r)) continue;
-			*o = conv_sample<Out, K, Out, FXP>(&sMid[ly * CONV_TW + lx], CONV_TW, taps.vt, ks);
+			*o = conv_sample<Out, K, Out, FXP, KS>(&sMid[ly * CONV_TW + lx], CONV_TW, vtTaps, ks);
 		}
 		else if (border == CVB200_BORDER_TYPE_ZERO) {
 			*o = 0;
@@ -142,7 +159,10 @@ static int convlt1_launch(const In* in, size_t width, size_t height, size_t stri
 	const int r = static_cast<int>(kernSize >> 1);
 	const size_t tw = CONV_TW + 2 * r, th = CONV_TH + 2 * r;
 	const size_t smem = ((tw * th * sizeof(In) + 15) & ~static_cast<size_t>(15)) + CONV_TW * th * sizeof(Out);
-	auto kern = convlt1_kernel<In, K, Out, FXP>;
+	auto kern = convlt1_kernel<In, K, Out, FXP, 0>;
+	if (kernSize == 3) kern = convlt1_kernel<In, K, Out, FXP, 3>;       // the sizes the reference's callers use (Sobel 3, Gaussian 5 / 7, adaptive mean 5)
+	else if (kernSize == 5) kern = convlt1_kernel<In, K, Out, FXP, 5>;
+	else if (kernSize == 7) kern = convlt1_kernel<In, K, Out, FXP, 7>;
 	if (smem > 48 * 1024) CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 	dim3 grid(static_cast<unsigned>(div_up(width, CONV_TW)), static_cast<unsigned>(div_up(height, CONV_TH)), static_cast<unsigned>(batch));
 	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
