@@ -125,3 +125,36 @@ def test_cuda_canny_then_kht_batched_on_device(cvb):
     for k in range(batch):
         want, _ = oracle.hough_kht("orc", canny_edges(frames[k]), 1.0, 1.0, 100)
         same_lines(got[k], want)
+
+
+def serpentine(w, h):
+    """One 8-connected string several thousand pixels long (longer than the linking kernel's shared-memory stage)."""
+    e = np.zeros((h, w), np.uint8)
+    left = True
+    for y in range(10, h - 10, 4):
+        e[y, 20:w - 20] = 255
+        x = w - 21 if left else 20
+        if y + 4 < h - 10:
+            e[y:y + 4, x] = 255
+        left = not left
+    return e
+
+
+@needs_ref
+def test_oracle_kht_long_string_vs_reference():
+    e = serpentine(320, 200)
+    assert (e != 0).sum() > 4096
+    a, gsa = oracle.hough_kht("orc", e, 1.0, 1.0, 10)
+    r, gsr = oracle.hough_kht("ref", e, 1.0, 1.0, 10, threads=1)
+    same_lines(a, r)
+    assert gsa == gsr
+
+
+@pytest.mark.gpu
+def test_cuda_kht_long_string(cvb):
+    from compv_b200 import _ffi
+    d = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 10)
+    for (w, h) in [(320, 200), (640, 480)]:
+        e = serpentine(w, h)
+        o, _ = oracle.hough_kht("orc", e, 1.0, 1.0, 10)
+        same_lines(d.process(e), o)
