@@ -50,7 +50,7 @@ def kernel_split(fn, steps):
 
 def emit(row, batch, ms, extra):
     px = batch * W * H
-    d = {"row": row, "workload": extra.pop("workload"), "frames": batch, "ms_per_batch": round(ms, 4), "Mpixels_per_s": round(px / ms / 1e3, 1)}
+    d = {"row": row, "workload": extra.pop("workload").replace("1080p", "%dx%d" % (W, H)), "frames": batch, "ms_per_batch": round(ms, 4), "Mpixels_per_s": round(px / ms / 1e3, 1)}
     d.update(extra)
     print(json.dumps(d), flush=True)
 
@@ -301,7 +301,10 @@ if __name__ == "__main__":
     ap.add_argument("--rows", default="convlt,sobel,gradient,fast,hog,threshold,sht,lsl,mser")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--size", default="1080p", choices=["1080p", "4k"])
     args = ap.parse_args()
+    if args.size == "4k":
+        W, H = 3840, 2160
     cvb.init(0)
     t0 = time.time()
     for r in args.rows.split(","):
