@@ -358,6 +358,32 @@ class CompVConnectedComponentLabeling:
             pass
 
 
+# ---- section 8f next row 1: CompVMathMorph -----------------------------------------------------------------
+def morph_strel(size, strel_type):
+    """CompVMathMorph::buildStructuringElement((width, height), type) -> (height, width) uint8."""
+    sw, sh = size
+    out = np.zeros((sh, sw), np.uint8)
+    check(lib().cvb200_morph_build_strel(vp(out), sz(sw), sz(sh), sz(sw), int(strel_type)), "cvb200_morph_build_strel")
+    return out
+
+
+def morph(img, strel, op, border=BORDER_TYPE_REPLICATE, width=None, fill=0):
+    """CompVMathMorph::process on a host frame; `fill` pre-fills the output (visible only with border IGNORE)."""
+    w, h, stride = _frame(img, width)
+    strel = np.ascontiguousarray(strel, np.uint8)
+    sh, sw = strel.shape
+    out = np.full((h, stride), fill, np.uint8)
+    check(lib().cvb200_morph_process(vp(img), sz(w), sz(h), sz(stride), vp(strel), sz(sw), sz(sh), sz(sw), vp(out), int(op), int(border)), "cvb200_morph_process")
+    return out
+
+
+def morph_dev(d_in, width, height, stride, strel, op, d_out, border=BORDER_TYPE_REPLICATE, batch=1, frame_pitch=0, stream=0):
+    strel = np.ascontiguousarray(strel, np.uint8)
+    sh, sw = strel.shape
+    check(lib().cvb200_morph_process_dev(vp(d_in), sz(width), sz(height), sz(stride), vp(strel), sz(sw), sz(sh), sz(sw), vp(d_out), int(op), int(border), sz(batch), sz(frame_pitch),
+                                         C.c_void_p(stream)), "cvb200_morph_process_dev")
+
+
 def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
     """Host frames (batch, height, stride) -> list of per-frame line arrays; cvb200_canny_kht_process_batch."""
     assert images.ndim == 3 and images.flags.c_contiguous

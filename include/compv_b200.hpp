@@ -374,4 +374,23 @@ struct CompVMathConvlt {
 	static COMPV_ERROR_CODE convlt1FixedPoint(const uint8_t* in, size_t w, size_t h, size_t stride, const uint16_t* vt, const uint16_t* hz, size_t ks, uint8_t* out, COMPV_BORDER_TYPE b = COMPV_BORDER_TYPE_ZERO) { return cvb200_convlt1_fxp_8u16u8u(in, w, h, stride, vt, hz, ks, out, b); }
 };
 
+// ---- CompVMathMorph (base/include/compv/base/math/compv_math_morph.h) ----
+enum COMPV_MATH_MORPH_STREL_TYPE { COMPV_MATH_MORPH_STREL_TYPE_RECT = CVB200_MATH_MORPH_STREL_TYPE_RECT, COMPV_MATH_MORPH_STREL_TYPE_DIAMOND = CVB200_MATH_MORPH_STREL_TYPE_DIAMOND,
+	COMPV_MATH_MORPH_STREL_TYPE_CROSS = CVB200_MATH_MORPH_STREL_TYPE_CROSS };
+enum COMPV_MATH_MORPH_OP_TYPE { COMPV_MATH_MORPH_OP_TYPE_ERODE = CVB200_MATH_MORPH_OP_TYPE_ERODE, COMPV_MATH_MORPH_OP_TYPE_DILATE = CVB200_MATH_MORPH_OP_TYPE_DILATE,
+	COMPV_MATH_MORPH_OP_TYPE_OPEN = CVB200_MATH_MORPH_OP_TYPE_OPEN, COMPV_MATH_MORPH_OP_TYPE_CLOSE = CVB200_MATH_MORPH_OP_TYPE_CLOSE };
+struct CompVMathMorph {
+	static COMPV_ERROR_CODE buildStructuringElement(CompVMatPtrPtr strel, const CompVSizeSz size, COMPV_MATH_MORPH_STREL_TYPE type = COMPV_MATH_MORPH_STREL_TYPE_RECT) {
+		COMPV_CHECK_EXP_RETURN(!strel || !size.width || !size.height, COMPV_ERROR_CODE_E_INVALID_PARAMETER);
+		COMPV_CHECK_CODE_RETURN(CompVMat::newObj<uint8_t>(strel, size.height, size.width));
+		return cvb200_morph_build_strel((*strel)->ptr<uint8_t>(), size.width, size.height, (*strel)->stride(), type);
+	}
+	static COMPV_ERROR_CODE process(const CompVMatPtr& input, const CompVMatPtr& strel, CompVMatPtrPtr output, COMPV_MATH_MORPH_OP_TYPE opType, COMPV_BORDER_TYPE borderType = COMPV_BORDER_TYPE_REPLICATE) {
+		COMPV_CHECK_EXP_RETURN(!compv_is_8u1(input) || !compv_is_8u1(strel) || !output || input == *output, COMPV_ERROR_CODE_E_INVALID_PARAMETER); // compv_math_morph.cxx:131-142
+		COMPV_CHECK_CODE_RETURN(CompVMat::newObj<uint8_t>(output, input->rows(), input->cols(), input->stride()));
+		return cvb200_morph_process(input->ptr<uint8_t>(), input->cols(), input->rows(), input->stride(), strel->ptr<uint8_t>(), strel->cols(), strel->rows(), strel->stride(),
+			(*output)->ptr<uint8_t>(), opType, borderType);
+	}
+};
+
 } // namespace compv

@@ -339,6 +339,25 @@ CVB200_API int cvb200_ccl_result_bounding_boxes(const cvb200_ccl_result_t* resul
  * ============================================================================================== */
 CVB200_API int cvb200_ccl_result_regions(const cvb200_ccl_result_t* result, const int32_t** sizes, const cvb200_rect16_t** boxes, const int16_t** points, size_t* regionCount, size_t* pointCount);
 
+/* ================================================================================================
+ * Section 8f "next" row 1 -- mathematical morphology. Replaces CompVMathMorph::buildStructuringElement / ::process (base/math/compv_math_morph.cxx:85-126):
+ * erode / dilate = min / max over the non-zero cells of the structuring element, open = erode then dilate, close = dilate then erode, with the reference's
+ * border handling (basicOper :128-240, addBordersVt :585-629 -- (strelHeight+1)/2 rows --, addBordersHz :631-694). 8-bit only, like the reference (:57 CompVMathMorphT).
+ * strel: HOST pointer, strelHeight rows of strelStride bytes; out may not alias in (:142). borderType: CVB200_BORDER_TYPE_* (IGNORE leaves the border cells of `out` untouched).
+ * ============================================================================================== */
+#define CVB200_MATH_MORPH_STREL_TYPE_RECT    0   /* COMPV_MATH_MORPH_STREL_TYPE (compv_common.h:402-406) */
+#define CVB200_MATH_MORPH_STREL_TYPE_DIAMOND 1
+#define CVB200_MATH_MORPH_STREL_TYPE_CROSS   2
+#define CVB200_MATH_MORPH_OP_TYPE_ERODE      0   /* COMPV_MATH_MORPH_OP_TYPE (compv_common.h:410-419); the others return E_NOT_IMPLEMENTED as in the reference (:119-122) */
+#define CVB200_MATH_MORPH_OP_TYPE_DILATE     1
+#define CVB200_MATH_MORPH_OP_TYPE_OPEN       2
+#define CVB200_MATH_MORPH_OP_TYPE_CLOSE      3
+CVB200_API int cvb200_morph_build_strel(uint8_t* strel, size_t width, size_t height, size_t strelStride, int type);
+CVB200_API int cvb200_morph_process(const uint8_t* in, size_t width, size_t height, size_t stride, const uint8_t* strel, size_t strelWidth, size_t strelHeight, size_t strelStride,
+	uint8_t* out, int opType, int borderType);
+CVB200_API int cvb200_morph_process_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const uint8_t* strel, size_t strelWidth, size_t strelHeight, size_t strelStride,
+	uint8_t* out, int opType, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
+
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
 CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);

@@ -345,6 +345,36 @@ def ccl_lmser(which, img, delta=2, min_area=0.0055 * 0.0055, max_area=0.8 * 0.15
     return out
 
 
+STREL_RECT, STREL_DIAMOND, STREL_CROSS = 0, 1, 2
+MORPH_ERODE, MORPH_DILATE, MORPH_OPEN, MORPH_CLOSE = 0, 1, 2, 3
+
+
+def morph_strel(which, size, strel_type):
+    """CompVMathMorph::buildStructuringElement: (height, width) uint8 array."""
+    sw, sh = size
+    out = np.zeros((sh, sw), np.uint8)
+    if which == "orc":
+        _chk(orc().orc_morph_strel(_p(out), _sz(sw), _sz(sh), int(strel_type)), "orc_morph_strel")
+    else:
+        dummy = np.zeros((max(sh, 1), max(sw, 1)), np.uint8)
+        _chk(ref(1).ref_morph(_p(dummy), _sz(sw), _sz(sh), _sz(sw), int(strel_type), None, _sz(sw), _sz(sh), _p(out), 0, 0, None, 0, None), "ref_morph")
+    return out
+
+
+def morph(which, img, strel, op, border=2, width=None, fill=0, threads=1, iters=0):
+    """CompVMathMorph::process with an explicit structuring element.  `fill`: value the output is pre-filled with (visible only with border IGNORE)."""
+    w, h, stride = _frame_args(img, width)
+    strel = np.ascontiguousarray(strel, np.uint8)
+    sh, sw = strel.shape
+    out = np.full((h, stride), fill, np.uint8)
+    if which == "orc":
+        _chk(orc().orc_morph_process(_p(img), _sz(w), _sz(h), _sz(stride), _p(strel), _sz(sw), _sz(sh), _sz(sw), _p(out), int(op), int(border)), "orc_morph_process")
+        return out
+    ms = np.zeros(max(iters, 1), np.float64)
+    _chk(ref(threads).ref_morph(_p(img), _sz(w), _sz(h), _sz(stride), -1, _p(strel), _sz(sw), _sz(sh), None, int(op), int(border), _p(out), int(iters), _p(ms)), "ref_morph")
+    return (out, ms[:iters]) if iters else out
+
+
 def histogram(img, width=None):
     w, h, stride = _frame_args(img, width)
     hist = np.zeros(256, np.uint32)

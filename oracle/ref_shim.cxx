@@ -12,6 +12,7 @@
 #include "compv/base/math/compv_math_convlt.h"
 #include "compv/base/math/compv_math_gauss.h"
 #include "compv/base/math/compv_math_utils.h"
+#include "compv/base/math/compv_math_morph.h"
 #include "compv/base/compv_gradient_fast.h"
 #include "compv/base/parallel/compv_parallel.h"
 #include "compv/core/compv_core.h"
@@ -477,6 +478,33 @@ int ref_ccl_lmser(const uint8_t* img, size_t w, size_t h, size_t stride, int del
 	}
 	if (regionCount) *regionCount = regions.size();
 	if (pointCount) *pointCount = np;
+	return 0;
+}
+
+// ---- section 8f "next" row 1: CompVMathMorph (base/math/compv_math_morph.cxx:85-126) ----
+// strelType >= 0: CompVMathMorph::buildStructuringElement(size sw x sh, type); strelType < 0: `strel` (sh x sw, packed) is used as is.
+// out is pre-filled by the caller (border IGNORE leaves cells untouched); op / border are the reference's enum values.
+int ref_morph(const uint8_t* img, size_t w, size_t h, size_t stride, int strelType, const uint8_t* strel, size_t sw, size_t sh, uint8_t* strelOut, int op, int border, uint8_t* outPtr,
+	int iters, double* msOut)
+{
+	CompVMatPtr image, se, out;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	if (strelType >= 0) SHIM_CHECK(CompVMathMorph::buildStructuringElement(&se, CompVSizeSz(sw, sh), static_cast<COMPV_MATH_MORPH_STREL_TYPE>(strelType)));
+	else {
+		SHIM_CHECK(CompVMat::newObjAligned<uint8_t>(&se, sh, sw));
+		for (size_t j = 0; j < sh; ++j) memcpy(se->ptr<uint8_t>(j), strel + j * sw, sw);
+	}
+	if (strelOut) for (size_t j = 0; j < sh; ++j) memcpy(strelOut + j * sw, se->ptr<const uint8_t>(j), sw);
+	if (!outPtr) return 0;
+	r = wrap8u(outPtr, w, h, stride, &out); // pre-filled output with the input's geometry: reused by basicOper (:144-148)
+	if (r) return r;
+	for (int it = -1; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(CompVMathMorph::process(image, se, &out, static_cast<COMPV_MATH_MORPH_OP_TYPE>(op), static_cast<COMPV_BORDER_TYPE>(border)));
+		if (it >= 0 && msOut) msOut[it] = now_ms() - t0;
+	}
+	copy_rows(out, outPtr, stride);
 	return 0;
 }
 

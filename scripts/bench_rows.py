@@ -294,11 +294,29 @@ def row_threshold(args):
     simple_row(args, "a10", "adaptive threshold, 5x5 fixed-point mean, delta 8, 1080p", 2, adaptive, r2)
 
 
-ROWS = {"convlt": row_convlt, "sobel": row_sobel, "gradient": row_gradient, "fast": row_fast, "hog": row_hog, "threshold": row_threshold, "sht": row_sht, "lsl": row_lsl, "mser": row_mser}
+def row_morph(args):
+    import oracle
+    frames = np.stack([((frame_text(W, H, 20 + k) < 128) * 255).astype(np.uint8) for k in range(min(args.batch, 8))])
+    d_in = torch.from_numpy(frames).cuda()
+    d_in = d_in.repeat((args.batch + len(frames) - 1) // len(frames), 1, 1)[:args.batch].contiguous()
+    d_out = torch.empty_like(d_in)
+    stream = torch.cuda.current_stream().cuda_stream
+    se = cvb.morph_strel((3, 3), 0)
+
+    def step():
+        cvb.morph_dev(d_in, W, H, W, se, 3, d_out, batch=args.batch, stream=stream)
+    ref = None
+    if oracle.have_ref():
+        _, t = oracle.morph("ref", frames[0], se, 3, threads=-1, iters=5)
+        ref = float(np.median(t))
+    simple_row(args, "8f-1", "morphological close, 3x3 rectangle (text pipeline step between threshold and PLSL), 1080p", 4, step, ref)
+
+
+ROWS = {"morph": row_morph, "convlt": row_convlt, "sobel": row_sobel, "gradient": row_gradient, "fast": row_fast, "hog": row_hog, "threshold": row_threshold, "sht": row_sht, "lsl": row_lsl, "mser": row_mser}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", default="convlt,sobel,gradient,fast,hog,threshold,sht,lsl,mser")
+    ap.add_argument("--rows", default="convlt,sobel,gradient,fast,hog,threshold,morph,sht,lsl,mser")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--size", default="1080p", choices=["1080p", "4k"])
