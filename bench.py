@@ -236,8 +236,16 @@ def main():
         # the dominant kernel by device time; every launch of it processes the whole batch
         alg_bytes = ALG_BYTES_PER_PX.get(top, 1.0) * B * W * H
         achieved = alg_bytes / (kernels[top]["avg_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:  # dram bytes read + written by that kernel in one `ncu --set full` capture of this command (profiles/), scaled to this launch's frame count
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+            if top in tj["bytes_per_launch"]:
+                traffic = tj["bytes_per_launch"][top] * B / tj["frames_per_launch"]
+                traffic_src = tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": how, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": kernels[top]["avg_ms"],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": how, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": kernels[top]["avg_ms"],
                 "note": "kht_link is the order-dependent linking walk (one warp per frame): latency-bound by construction, see DESIGN.md" if top == "kht_link" else ""}
         if "canny_front" in kernels and top != "canny_front":
             cf = ALG_BYTES_PER_PX["canny_front"] * B * W * H / (kernels["canny_front"]["avg_ms"] * 1e-3) / 1e9
