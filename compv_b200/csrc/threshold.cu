@@ -97,11 +97,19 @@ __global__ void threshold_global_kernel(const uint8_t* __restrict__ in, uint8_t*
 constexpr int AD_TW = 64, AD_TH = 32, AD_THREADS = 256, AD_MAX_TAPS = 63;
 struct AdaptTaps { uint16_t vt[AD_MAX_TAPS]; uint16_t hz[AD_MAX_TAPS]; };
 
+// KS > 0: compile-time kernel size (the block sizes callers use: 3, 5, 7), taps in registers, loops unrolled; KS == 0: any odd size
+template <int KS>
 __global__ void __launch_bounds__(AD_THREADS)
-threshold_adaptive_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H, size_t stride, size_t framePitch, const AdaptTaps taps, int ks,
+threshold_adaptive_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H, size_t stride, size_t framePitch, const AdaptTaps taps, int ksRuntime,
 	int deltaInt, int maxVal, int invert)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int ks = KS > 0 ? KS : ksRuntime;
+	unsigned int hzR[KS > 0 ? KS : 1], vtR[KS > 0 ? KS : 1];
+	if (KS > 0) {
+		#pragma unroll
+		for (int k = 0; k < KS; ++k) { hzR[k] = taps.hz[k]; vtR[k] = taps.vt[k]; }
+	}
 	const int r = ks >> 1;
 	const int tw = AD_TW + 2 * r, th = AD_TH + 2 * r;
 	uint8_t* sIn = smem_raw;
@@ -109,10 +117,14 @@ threshold_adaptive_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ 
 	const int x0 = blockIdx.x * AD_TW, y0 = blockIdx.y * AD_TH;
 	in += blockIdx.z * framePitch; out += blockIdx.z * framePitch;
 	const int tid = threadIdx.x;
-	for (int i = tid; i < tw * th; i += AD_THREADS) {
-		const int ly = i / tw, lx = i - ly * tw;
-		const int gx = x0 - r + lx, gy = y0 - r + ly;
-		sIn[i] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? in[static_cast<size_t>(gy) * stride + gx] : 0;
+	for (int ly = tid >> 5; ly < th; ly += AD_THREADS / 32) { // one warp per tile row: no division
+		const int gy = y0 - r + ly;
+		const bool rowIn = (gy >= 0 && gy < H);
+		const uint8_t* src = in + static_cast<size_t>(rowIn ? gy : 0) * stride;
+		for (int lx = tid & 31; lx < tw; lx += 32) {
+			const int gx = x0 - r + lx;
+			sIn[ly * tw + lx] = (rowIn && gx >= 0 && gx < W) ? src[gx] : 0;
+		}
 	}
 	__syncthreads();
 	// horizontal fixed-point mean (compv_math_convlt.h:386-405), zero on the r-wide column border
@@ -122,7 +134,8 @@ threshold_adaptive_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ 
 		unsigned int sum = 0;
 		if (gy >= 0 && gy < H && gx >= r && gx < W - r) {
 			const uint8_t* p = &sIn[ly * tw + lx];
-			for (int k = 0; k < ks; ++k) sum += (static_cast<unsigned int>(p[k]) * taps.hz[k]) >> 16;
+			#pragma unroll
+			for (int k = 0; k < ks; ++k) sum += (static_cast<unsigned int>(p[k]) * (KS > 0 ? hzR[KS > 0 ? k : 0] : static_cast<unsigned int>(taps.hz[k]))) >> 16;
 			sum = sum > 255u ? 255u : sum;
 		}
 		sMid[i] = static_cast<uint8_t>(sum);
@@ -137,7 +150,8 @@ threshold_adaptive_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ 
 		unsigned int mean = 0;
 		if (gy >= r && gy < H - r) {
 			const uint8_t* p = &sMid[ly * AD_TW + lx];
-			for (int k = 0; k < ks; ++k) mean += (static_cast<unsigned int>(p[k * AD_TW]) * taps.vt[k]) >> 16;
+			#pragma unroll
+			for (int k = 0; k < ks; ++k) mean += (static_cast<unsigned int>(p[k * AD_TW]) * (KS > 0 ? vtR[KS > 0 ? k : 0] : static_cast<unsigned int>(taps.vt[k]))) >> 16;
 			mean = mean > 255u ? 255u : mean;
 		}
 		const int idx = static_cast<int>(sIn[(ly + r) * tw + lx + r]) - static_cast<int>(mean) + 255;
@@ -242,11 +256,15 @@ static int adaptive_launch(const uint8_t* in, size_t width, size_t height, size_
 	const int r = static_cast<int>(kernSize >> 1);
 	const size_t tw = AD_TW + 2 * r, th = AD_TH + 2 * r;
 	const size_t smem = ((tw * th + 15) & ~static_cast<size_t>(15)) + AD_TW * th;
-	if (smem > 48 * 1024) CVB_CUDA(cudaFuncSetAttribute(threshold_adaptive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	auto kern = threshold_adaptive_kernel<0>;
+	if (kernSize == 3) kern = threshold_adaptive_kernel<3>;
+	else if (kernSize == 5) kern = threshold_adaptive_kernel<5>;
+	else if (kernSize == 7) kern = threshold_adaptive_kernel<7>;
+	if (smem > 48 * 1024) CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 	dim3 grid(static_cast<unsigned>(div_up(width, AD_TW)), static_cast<unsigned>(div_up(height, AD_TH)), static_cast<unsigned>(batch));
 	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 	{ KernelScope ks_("threshold_adaptive", stream);
-	  threshold_adaptive_kernel<<<grid, AD_THREADS, smem, stream>>>(in, out, static_cast<int>(width), static_cast<int>(height), stride, framePitch ? framePitch : stride * height,
+	  kern<<<grid, AD_THREADS, smem, stream>>>(in, out, static_cast<int>(width), static_cast<int>(height), stride, framePitch ? framePitch : stride * height,
 		taps, static_cast<int>(kernSize), deltaInt, maxValU8, invert ? 1 : 0); }
 	CVB_LAUNCHED();
 	return CVB200_S_OK;

@@ -10,13 +10,15 @@
 // CompVHough / CompVHOG (base/include/compv/base/compv_features.h:160-240), CompVConnectedComponentLabeling + results (base/include/compv/base/compv_ccl.h:105-241),
 // CompVImage::threshold* (base/include/compv/base/image/compv_image.h:63-67), CompVMathConvlt::convlt1 (base/include/compv/base/math/compv_math_convlt.h:25-55).
 // Header only; link with -lcompv_b200.  Everything computes on the GPU: there is no CPU path behind these classes (calls fail with E_NOT_INITIALIZED / E_CUDA).
-// Not mirrored ("next"): toCartesian, extract, the threading runtime, image formats other than 8-bit gray.
+// Host-side helpers of the results are here too (CompVHough::toCartesian, CompVConnectedComponentLabelingResult::extract, CompVMathMorph).
+// Not mirrored: the threading runtime, image formats other than 8-bit gray, ORB / pyramids.
 #pragma once
 
 #include "cvb200.h"
 
 #include <cstdint>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -192,6 +194,9 @@ private:
 // ---- CompVHough (compv_features.h:217-227) ----
 typedef cvb200_hough_line_t CompVHoughLine; // {rho, theta, strength} (compv_common.h:686-692)
 typedef std::vector<CompVHoughLine> CompVHoughLineVector;
+struct CompVPointFloat32 { float x, y, z; };
+struct CompVLineFloat32 { CompVPointFloat32 a, b; };
+typedef std::vector<CompVLineFloat32> CompVLineFloat32Vector;
 class CompVHough;
 typedef std::shared_ptr<CompVHough> CompVHoughPtr;
 typedef CompVHoughPtr* CompVHoughPtrPtr;
@@ -217,13 +222,40 @@ public:
 		COMPV_CHECK_EXP_RETURN(!hough, COMPV_ERROR_CODE_E_INVALID_PARAMETER);
 		cvb200_hough_t* h = NULL;
 		COMPV_CHECK_CODE_RETURN(cvb200_hough_new(&h, id, rho, theta, threshold));
-		hough->reset(new CompVHough(h));
+		hough->reset(new CompVHough(h, id));
+		return COMPV_ERROR_CODE_S_OK;
+	}
+	// Polar (rho, theta) -> the two points where the line crosses x = 0 and x = width (or a vertical line when theta == 0).  Host arithmetic, as in the reference:
+	// KHT measures rho from the image centre (houghkht.cxx:1249-1280), SHT from the origin (houghsht.cxx:566-592).
+	COMPV_ERROR_CODE toCartesian(const size_t imageWidth, const size_t imageHeight, const CompVHoughLineVector& polar, CompVLineFloat32Vector& cartesian) const {
+		COMPV_CHECK_EXP_RETURN(!imageWidth || !imageHeight, COMPV_ERROR_CODE_E_INVALID_PARAMETER);
+		cartesian.resize(polar.size());
+		const float widthF = static_cast<float>(imageWidth), heightF = static_cast<float>(imageHeight);
+		const float r = std::sqrt((widthF * widthF) + (heightF * heightF));
+		const bool centred = (m_id == COMPV_HOUGHKHT_ID);
+		const float ox = centred ? widthF * 0.5f : 0.f, oy = centred ? heightF * 0.5f : 0.f;
+		for (size_t i = 0; i < polar.size(); ++i) {
+			const float rho = polar[i].rho, theta = polar[i].theta;
+			CompVLineFloat32& l = cartesian[i];
+			if (theta == 0.f) { l.a.x = l.b.x = rho + ox; l.a.y = r; l.b.y = -r; }
+			else if (centred) {
+				const float a = std::cos(theta) * ox, b = 1.f / std::sin(theta);
+				l.a.x = 0.f; l.a.y = ((rho + a) * b) + oy;
+				l.b.x = widthF; l.b.y = ((rho - a) * b) + oy;
+			}
+			else {
+				const float a = std::cos(theta), b = 1.f / std::sin(theta);
+				l.a.x = 0.f; l.a.y = rho * b;
+				l.b.x = widthF; l.b.y = (rho - (widthF * a)) * b;
+			}
+			l.a.z = l.b.z = 1.f;
+		}
 		return COMPV_ERROR_CODE_S_OK;
 	}
 	cvb200_hough_t* handle() { return m_h; }
 private:
-	explicit CompVHough(cvb200_hough_t* h) : m_h(h) {}
-	cvb200_hough_t* m_h;
+	CompVHough(cvb200_hough_t* h, int id) : m_h(h), m_id(id) {}
+	cvb200_hough_t* m_h; int m_id;
 };
 
 // ---- CompVHOG (compv_features.h:229-240) ----
@@ -264,6 +296,8 @@ typedef cvb200_rect16_t CompVConnectedComponentBoundingBox; // CompVRectInt16 {l
 typedef std::vector<CompVConnectedComponentBoundingBox> CompVConnectedComponentBoundingBoxesVector;
 struct CompVPoint2DInt16 { int16_t x, y; };
 typedef std::vector<CompVPoint2DInt16> CompVConnectedComponentPoints;
+typedef std::vector<CompVConnectedComponentPoints> CompVConnectedComponentPointsVector;
+enum COMPV_CCL_EXTRACT_TYPE { COMPV_CCL_EXTRACT_TYPE_SEGMENT, COMPV_CCL_EXTRACT_TYPE_BLOB };
 struct CompVConnectedComponentLabelingRegionMser { CompVConnectedComponentPoints points; CompVConnectedComponentBoundingBox boundingBox; };
 typedef std::vector<CompVConnectedComponentLabelingRegionMser> CompVConnectedComponentLabelingRegionMserVector;
 
@@ -294,6 +328,29 @@ public:
 		COMPV_CHECK_EXP_RETURN(m_id != COMPV_PLSL_ID, COMPV_ERROR_CODE_E_NOT_IMPLEMENTED);
 		COMPV_CHECK_CODE_RETURN(CompVMat::newObj<int32_t>(ptr32sLabels, m_height, m_width, m_width)); // strideless, like the reference (ccl_lsl_result.cxx:62)
 		return cvb200_ccl_result_flatten(m_h, (*ptr32sLabels)->ptr<int32_t>(), m_width);
+	}
+	// extract (ccl_lsl_result.cxx:100-134, 308-416): per label, every pixel (BLOB) or the two end points {start, y}, {end, y} of every run (SEGMENT), rows top-down, runs
+	// left to right -- the order of the reference's single-threaded fill (its threaded fill orders rows by arrival).
+	COMPV_ERROR_CODE extract(CompVConnectedComponentPointsVector& points, COMPV_CCL_EXTRACT_TYPE type = COMPV_CCL_EXTRACT_TYPE_BLOB) const {
+		points.clear();
+		COMPV_CHECK_EXP_RETURN(m_id != COMPV_PLSL_ID, COMPV_ERROR_CODE_E_NOT_IMPLEMENTED); // lmser_result.cxx:41-45
+		COMPV_CHECK_EXP_RETURN(type != COMPV_CCL_EXTRACT_TYPE_SEGMENT && type != COMPV_CCL_EXTRACT_TYPE_BLOB, COMPV_ERROR_CODE_E_INVALID_PARAMETER);
+		const uint32_t* rowOffsets; const cvb200_ccl_range_t* ranges; size_t n = 0;
+		COMPV_CHECK_CODE_RETURN(cvb200_ccl_result_segments(m_h, &rowOffsets, &ranges, &n));
+		if (!labelsCount()) return COMPV_ERROR_CODE_S_OK;
+		points.resize(labelsCount());
+		std::vector<size_t> counts(points.size(), 0);
+		for (size_t s = 0; s < n; ++s) counts[static_cast<size_t>(ranges[s].a - 1)] += (type == COMPV_CCL_EXTRACT_TYPE_BLOB) ? static_cast<size_t>(ranges[s].end - ranges[s].start) : 2;
+		for (size_t a = 0; a < points.size(); ++a) points[a].reserve(counts[a]);
+		for (size_t j = 0; j < m_height; ++j) {
+			for (uint32_t s = rowOffsets[j]; s < rowOffsets[j + 1]; ++s) {
+				CompVConnectedComponentPoints& pp = points[static_cast<size_t>(ranges[s].a - 1)];
+				CompVPoint2DInt16 pt; pt.y = static_cast<int16_t>(j);
+				if (type == COMPV_CCL_EXTRACT_TYPE_BLOB) for (int16_t x = ranges[s].start; x < ranges[s].end; ++x) { pt.x = x; pp.push_back(pt); }
+				else { pt.x = ranges[s].start; pp.push_back(pt); pt.x = ranges[s].end; pp.push_back(pt); }
+			}
+		}
+		return COMPV_ERROR_CODE_S_OK;
 	}
 	// CompVConnectedComponentLabelingResultLMSER::points() / boundingBoxes()
 	COMPV_ERROR_CODE points(CompVConnectedComponentLabelingRegionMserVector& regions) const {

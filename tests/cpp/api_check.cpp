@@ -48,6 +48,9 @@ static COMPV_ERROR_CODE run(size_t width, size_t height, const char* framePath, 
 	CompVHoughLineVector lines;
 	COMPV_CHECK_CODE_RETURN(hough->process(edges, lines));
 	COMPV_CHECK_EXP_RETURN(!dump(out + "/kht_lines.bin", lines.data(), lines.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
+	CompVLineFloat32Vector cart;
+	COMPV_CHECK_CODE_RETURN(hough->toCartesian(width, height, lines, cart));
+	COMPV_CHECK_EXP_RETURN(!dump(out + "/kht_cartesian.f32", reinterpret_cast<const float*>(cart.data()), cart.size() * 6), COMPV_ERROR_CODE_E_INVALID_STATE);
 	COMPV_CHECK_EXP_RETURN(hough->setFloat32(COMPV_HOUGH_SET_FLT32_RHO, 2.f) != COMPV_ERROR_CODE_E_INVALID_PARAMETER, COMPV_ERROR_CODE_E_INVALID_STATE); // houghkht.cxx:144
 
 	// FAST9, threshold 20, NMS, every corner (unittests/feature_fast.cxx)
@@ -77,6 +80,25 @@ static COMPV_ERROR_CODE run(size_t width, size_t height, const char* framePath, 
 	CompVConnectedComponentBoundingBoxesVector boxes;
 	COMPV_CHECK_CODE_RETURN(result->boundingBoxes(boxes));
 	COMPV_CHECK_EXP_RETURN(boxes.size() != result->labelsCount(), COMPV_ERROR_CODE_E_INVALID_STATE);
+	CompVConnectedComponentPointsVector blobs, segs;
+	COMPV_CHECK_CODE_RETURN(result->extract(blobs, COMPV_CCL_EXTRACT_TYPE_BLOB));
+	COMPV_CHECK_CODE_RETURN(result->extract(segs, COMPV_CCL_EXTRACT_TYPE_SEGMENT));
+	COMPV_CHECK_EXP_RETURN(blobs.size() != result->labelsCount() || segs.size() != blobs.size(), COMPV_ERROR_CODE_E_INVALID_STATE);
+	{
+		std::vector<int16_t> flat; // label, count, then (x, y) pairs, for the three largest-index labels
+		for (size_t a = blobs.size() > 3 ? blobs.size() - 3 : 0; a < blobs.size(); ++a) {
+			flat.push_back(static_cast<int16_t>(a + 1)); flat.push_back(static_cast<int16_t>(blobs[a].size()));
+			for (size_t k = 0; k < blobs[a].size(); ++k) { flat.push_back(blobs[a][k].x); flat.push_back(blobs[a][k].y); }
+		}
+		COMPV_CHECK_EXP_RETURN(!dump(out + "/plsl_blobs.i16", flat.data(), flat.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
+	}
+	// the text pipeline's clean-up step (samples/text_recognition/main.cxx:93-104)
+	CompVMatPtr strel, closed;
+	COMPV_CHECK_CODE_RETURN(CompVMathMorph::buildStructuringElement(&strel, CompVSizeSz(3, 3), COMPV_MATH_MORPH_STREL_TYPE_RECT));
+	COMPV_CHECK_CODE_RETURN(CompVMathMorph::process(binar, strel, &closed, COMPV_MATH_MORPH_OP_TYPE_CLOSE));
+	for (size_t j = 0; j < height; ++j) memcpy(&packed[j * width], closed->ptr<uint8_t>(j), width);
+	COMPV_CHECK_EXP_RETURN(!dump(out + "/closed.u8", packed.data(), packed.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
+	for (size_t j = 0; j < height; ++j) memcpy(&packed[j * width], binar->ptr<uint8_t>(j), width);
 	COMPV_CHECK_CODE_RETURN(ccl->process(binar, &result)); // the result object is reused (ccl_lsl.cxx:585-592)
 
 	// MSER with the unit test's parameters (unittests/ccl_mser.cxx:26-46)

@@ -41,6 +41,16 @@ def test_cpp_mirror_matches_the_oracle(tmp_path):
     assert len(lines) == len(want_lines) == 20
     for k in ("rho", "theta", "strength"):
         np.testing.assert_array_equal(lines[k], want_lines[k])
+    cart = np.fromfile(tmp_path / "kht_cartesian.f32", np.float32).reshape(-1, 6)
+    assert len(cart) == len(lines)
+    for (ax, ay, az, bx, by, bz), ln in zip(cart, lines):           # houghkht.cxx:1249-1280, restated in float32
+        rho, theta = np.float32(ln["rho"]), np.float32(ln["theta"])
+        assert az == 1 and bz == 1
+        if theta == 0:
+            assert ax == bx == rho + np.float32(w) * np.float32(0.5)
+        else:
+            a, b = np.cos(theta) * np.float32(w * 0.5), np.float32(1) / np.sin(theta)
+            np.testing.assert_allclose([ax, ay, bx, by], [0, (rho + a) * b + h * 0.5, w, (rho - a) * b + h * 0.5], rtol=1e-5, atol=1e-3)
     pts = np.fromfile(tmp_path / "fast_points.bin", POINT_DTYPE)
     want_pts = oracle.fast_detect("orc", img, 9, 20, True)
     assert len(pts) == len(want_pts) > 0
@@ -51,6 +61,16 @@ def test_cpp_mirror_matches_the_oracle(tmp_path):
     np.testing.assert_array_equal(otsu, want_otsu)
     labels = np.fromfile(tmp_path / "plsl_labels.i32", np.int32).reshape(h, w)
     np.testing.assert_array_equal(labels, oracle.ccl_lsl("orc", otsu)["labels"])
+    blobs = np.fromfile(tmp_path / "plsl_blobs.i16", np.int16)
+    i = 0
+    while i < len(blobs):                                            # extract(BLOB): every pixel of the label, rows top-down, left to right
+        a, n = int(blobs[i]), int(blobs[i + 1])
+        xy = blobs[i + 2:i + 2 + 2 * n].reshape(n, 2)
+        ys, xs = np.nonzero(labels == a)
+        np.testing.assert_array_equal(xy, np.stack([xs, ys], 1))
+        i += 2 + 2 * n
+    closed = np.fromfile(tmp_path / "closed.u8", np.uint8).reshape(h, w)
+    np.testing.assert_array_equal(closed, oracle.morph("orc", otsu, oracle.morph_strel("orc", (3, 3), oracle.STREL_RECT), oracle.MORPH_CLOSE))
     sizes = np.fromfile(tmp_path / "mser_sizes.i32", np.int32)
     want = oracle.ccl_lmser("orc", img)
     np.testing.assert_array_equal(np.sort(sizes), np.sort(want["sizes"]))
