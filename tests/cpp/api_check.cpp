@@ -85,12 +85,12 @@ static COMPV_ERROR_CODE run(size_t width, size_t height, const char* framePath, 
 	COMPV_CHECK_CODE_RETURN(result->extract(segs, COMPV_CCL_EXTRACT_TYPE_SEGMENT));
 	COMPV_CHECK_EXP_RETURN(blobs.size() != result->labelsCount() || segs.size() != blobs.size(), COMPV_ERROR_CODE_E_INVALID_STATE);
 	{
-		std::vector<int16_t> flat; // label, count, then (x, y) pairs, for the three largest-index labels
+		std::vector<int32_t> flat; // label, count, then (x, y) pairs, for the three largest-index labels
 		for (size_t a = blobs.size() > 3 ? blobs.size() - 3 : 0; a < blobs.size(); ++a) {
-			flat.push_back(static_cast<int16_t>(a + 1)); flat.push_back(static_cast<int16_t>(blobs[a].size()));
+			flat.push_back(static_cast<int32_t>(a + 1)); flat.push_back(static_cast<int32_t>(blobs[a].size()));
 			for (size_t k = 0; k < blobs[a].size(); ++k) { flat.push_back(blobs[a][k].x); flat.push_back(blobs[a][k].y); }
 		}
-		COMPV_CHECK_EXP_RETURN(!dump(out + "/plsl_blobs.i16", flat.data(), flat.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
+		COMPV_CHECK_EXP_RETURN(!dump(out + "/plsl_blobs.i32", flat.data(), flat.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
 	}
 	// the text pipeline's clean-up step (samples/text_recognition/main.cxx:93-104)
 	CompVMatPtr strel, closed;
