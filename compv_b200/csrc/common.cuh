@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <atomic>
+#include <functional>
 #include <mutex>
 
 #include "../../include/cvb200.h"
@@ -70,6 +71,10 @@ struct HostBuf {
 };
 
 static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// Persistent host worker pool for the per-frame host stages (the std::sort that fixes the Hough detectors' tie order): fn(i) for i in [0, n), the calling
+// thread takes part.  Workers are created once (at most 127) instead of per call; frames are handed out one at a time.
+void host_parallel_for(size_t n, const std::function<void(size_t)>& fn);
 
 // ---- device helpers ----
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -733,49 +733,34 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	// ---- host: sort + sweep (houghkht.cxx:1195-1247). std::sort of the same libstdc++ on the same input order = the reference's tie order ----
 	// Frames are independent: a few host threads share them (the sort of a few thousand cells per frame is the only per-frame host work).
 	const size_t lim = (h->maxLines <= 0) ? static_cast<size_t>(INT_MAX) : static_cast<size_t>(h->maxLines);
-	auto finishFrames = [&](size_t f0, size_t f1) {
-		std::vector<uint8_t> visited(accCells, 0);
-		for (size_t f = f0; f < f1; ++f) {
-			KhtVote* v = hv + f * votesCap;
-			const size_t nv = hf[f].nVotes;
-			std::sort(v, v + nv, [](const KhtVote& a, const KhtVote& b) { return a.count > b.count; });
-			size_t n = 0;
-			for (size_t i = 0; i < nv; ++i) {
-				uint8_t* pv = &visited[static_cast<size_t>(v[i].theta_index) * g.cs + v[i].rho_index];
-				const uint8_t* t = pv - g.cs; const uint8_t* b = pv + g.cs;
-				const bool seen = t[-1] || t[0] || t[1] || pv[-1] || pv[1] || b[-1] || b[0] || b[1];
-				if (!seen) {
-					if (n < lim) {
-						if (n < capacity) {
-							cvb200_hough_line_t& L = lines[f * capacity + n];
-							L.rho = static_cast<float>(rho[v[i].rho_index]);
-							L.theta = static_cast<float>((theta[v[i].theta_index] * M_PI) / 180.0);
-							L.strength = static_cast<size_t>(v[i].count);
-						}
-						++n;
+	host_parallel_for(batch, [&](size_t f) {
+		static thread_local std::vector<uint8_t> visited; // all zero between frames (the sweep clears what it marked)
+		if (visited.size() < accCells) visited.assign(accCells, 0);
+
+		KhtVote* v = hv + f * votesCap;
+		const size_t nv = hf[f].nVotes;
+		std::sort(v, v + nv, [](const KhtVote& a, const KhtVote& b) { return a.count > b.count; });
+		size_t n = 0;
+		for (size_t i = 0; i < nv; ++i) {
+			uint8_t* pv = &visited[static_cast<size_t>(v[i].theta_index) * g.cs + v[i].rho_index];
+			const uint8_t* t = pv - g.cs; const uint8_t* b = pv + g.cs;
+			const bool seen = t[-1] || t[0] || t[1] || pv[-1] || pv[1] || b[-1] || b[0] || b[1];
+			if (!seen) {
+				if (n < lim) {
+					if (n < capacity) {
+						cvb200_hough_line_t& L = lines[f * capacity + n];
+						L.rho = static_cast<float>(rho[v[i].rho_index]);
+						L.theta = static_cast<float>((theta[v[i].theta_index] * M_PI) / 180.0);
+						L.strength = static_cast<size_t>(v[i].count);
 					}
+					++n;
 				}
-				*pv = 0xff;
 			}
-			for (size_t i = 0; i < nv; ++i) visited[static_cast<size_t>(v[i].theta_index) * g.cs + v[i].rho_index] = 0;
-			counts[f] = n;
+			*pv = 0xff;
 		}
-	};
-	{
-		size_t nThreads = std::thread::hardware_concurrency();
-		if (nThreads > 64) nThreads = 64;
-		if (nThreads > batch) nThreads = batch;
-		if (nThreads <= 1) finishFrames(0, batch);
-		else {
-			std::vector<std::thread> pool;
-			const size_t per = div_up(batch, nThreads);
-			for (size_t t = 0; t < nThreads; ++t) {
-				const size_t f0 = t * per, f1 = std::min(batch, f0 + per);
-				if (f0 < f1) pool.emplace_back(finishFrames, f0, f1);
-			}
-			for (auto& th : pool) th.join();
-		}
-	}
+		for (size_t i = 0; i < nv; ++i) visited[static_cast<size_t>(v[i].theta_index) * g.cs + v[i].rho_index] = 0;
+		counts[f] = n;
+	});
 	{
 		const size_t f = batch - 1;
 		h->lastGs = (hf[f].nStr && hf[f].nClus) ? hf[f].gs : 1.0;

@@ -18,7 +18,6 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
-#include <thread>
 #include <vector>
 
 namespace cvb {
@@ -303,29 +302,14 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 
 	// ---- host: std::sort by strength + maxLines (houghsht.cxx:241-247) ----
 	const size_t lim = (h->maxLines <= 0) ? static_cast<size_t>(INT_MAX) : static_cast<size_t>(h->maxLines);
-	auto finishFrames = [&](size_t f0, size_t f1) {
-		for (size_t f = f0; f < f1; ++f) {
-			cvb200_hough_line_t* v = hp + hDesc[f].base;
-			size_t n = hDesc[f].total;
-			std::sort(v, v + n, [](const cvb200_hough_line_t& a, const cvb200_hough_line_t& b) -> bool { return a.strength > b.strength; });
-			if (n > lim) n = lim;
-			if (capacity) memcpy(lines + f * capacity, v, std::min(n, capacity) * sizeof(cvb200_hough_line_t));
-			counts[f] = n;
-		}
-	};
-	size_t nThreads = std::thread::hardware_concurrency();
-	if (nThreads > 16) nThreads = 16;
-	if (nThreads > batch) nThreads = batch;
-	if (nThreads <= 1) finishFrames(0, batch);
-	else {
-		std::vector<std::thread> pool;
-		const size_t per = div_up(batch, nThreads);
-		for (size_t t = 0; t < nThreads; ++t) {
-			const size_t f0 = t * per, f1 = std::min(batch, f0 + per);
-			if (f0 < f1) pool.emplace_back(finishFrames, f0, f1);
-		}
-		for (auto& th : pool) th.join();
-	}
+	host_parallel_for(batch, [&](size_t f) {
+		cvb200_hough_line_t* v = hp + hDesc[f].base;
+		size_t n = hDesc[f].total;
+		std::sort(v, v + n, [](const cvb200_hough_line_t& a, const cvb200_hough_line_t& b) -> bool { return a.strength > b.strength; });
+		if (n > lim) n = lim;
+		if (capacity) memcpy(lines + f * capacity, v, std::min(n, capacity) * sizeof(cvb200_hough_line_t));
+		counts[f] = n;
+	});
 	return CVB200_S_OK;
 }
 

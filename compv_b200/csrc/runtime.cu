@@ -2,6 +2,10 @@
 // Replaces the reference's CompVGpu::init probe (gpu/compv_gpu.cxx:36-62), which only dlopen()s libcuda and sets a flag.
 #include "common.cuh"
 
+#include <condition_variable>
+#include <thread>
+#include <vector>
+
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -236,3 +240,63 @@ int cvb200_stream_sync(cvb200_stream_t stream)
 }
 
 } // extern "C"
+
+// ---- host worker pool ----
+namespace cvb {
+namespace {
+struct HostPool {
+	std::vector<std::thread> workers;
+	std::mutex m;
+	std::condition_variable cvWork, cvDone;
+	const std::function<void(size_t)>* fn = nullptr;
+	std::atomic<size_t> next{0};
+	size_t n = 0, generation = 0, active = 0;
+	bool stop = false;
+	std::mutex callMutex; // one parallel_for at a time
+	void run() {
+		size_t seen = 0;
+		for (;;) {
+			const std::function<void(size_t)>* f;
+			size_t count;
+			{
+				std::unique_lock<std::mutex> lk(m);
+				cvWork.wait(lk, [&] { return stop || generation != seen; });
+				if (stop) return;
+				seen = generation; f = fn; count = n;
+			}
+			for (size_t i; (i = next.fetch_add(1, std::memory_order_relaxed)) < count;) (*f)(i);
+			{
+				std::lock_guard<std::mutex> lk(m);
+				if (--active == 0) cvDone.notify_all();
+			}
+		}
+	}
+	~HostPool() {
+		{ std::lock_guard<std::mutex> lk(m); stop = true; }
+		cvWork.notify_all();
+		for (auto& t : workers) t.join();
+	}
+};
+HostPool& host_pool() { static HostPool p; return p; }
+} // namespace
+
+void host_parallel_for(size_t n, const std::function<void(size_t)>& fn)
+{
+	if (n == 0) return;
+	HostPool& p = host_pool();
+	size_t want = std::thread::hardware_concurrency();
+	if (want > 128) want = 128;
+	if (want > n) want = n;
+	if (want <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+	std::lock_guard<std::mutex> call(p.callMutex);
+	while (p.workers.size() + 1 < want) p.workers.emplace_back([&p] { p.run(); });
+	{
+		std::lock_guard<std::mutex> lk(p.m);
+		p.fn = &fn; p.n = n; p.next.store(0); p.active = p.workers.size(); ++p.generation;
+	}
+	p.cvWork.notify_all();
+	for (size_t i; (i = p.next.fetch_add(1, std::memory_order_relaxed)) < n;) fn(i);
+	std::unique_lock<std::mutex> lk(p.m);
+	p.cvDone.wait(lk, [&] { return p.active == 0; });
+}
+} // namespace cvb
