@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=256, help="frames per rank per step (the KHT linking stage runs one warp per frame: throughput grows with frames in flight)")
+    ap.add_argument("--frames", type=int, default=512, help="frames per rank per step (the KHT linking stage runs one warp per frame: throughput grows with frames in flight)")
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames timed for cpu_baseline (rank 0, N=1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
