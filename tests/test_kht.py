@@ -161,15 +161,15 @@ def test_cuda_kht_long_string(cvb):
 
 
 @pytest.mark.gpu
-def test_cuda_canny_kht_host_batch_two_halves(cvb):
-    """cvb200_canny_kht_process_batch on a batch large enough to be cut in two concurrently linked halves (and not a multiple of the upload chunk)."""
+def test_cuda_canny_kht_host_batch_many_chunks(cvb):
+    """cvb200_canny_kht_process_batch on a batch that spans many upload chunks (and is not a multiple of the chunk size); called twice: cached streams and buffers are reused."""
     from compv_b200 import _ffi
     w, h, batch = 320, 200, 150
     frames = np.stack([frame_g(w, h, 500 + k) if k % 4 else frame_text(w, h, k) for k in range(batch)])
     canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
     canny.set_preblur(5, 1.0)
     kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 30)
-    for _ in range(2):   # second call: the cached twin object and streams are reused
+    for _ in range(2):
         got = cvb.canny_kht_process_batch(canny, kht, frames, width=w)
         gs_last = None
         for k in range(batch):
