@@ -315,6 +315,9 @@ canny_hysteresis_kernel(const HystParams p)
 	for (int k = 0; k < 16; ++k) if (row[k] == CLS_WEAK) weak |= (1u << k);
 	unsigned int promoted = 0;
 
+	// Chaotic relaxation: a thread reads its neighbours' cells while their owners may be promoting them (compute-sanitizer racecheck reports exactly this
+	// read/write pair, profiles/r1_compute_sanitizer_racecheck.log).  It is deliberate: cells only ever change weak -> strong (one byte store), a stale read merely
+	// postpones a promotion to the next sweep, and the loop runs until a full sweep changes nothing, so the fixed point -- the 8-connected closure -- is unique.
 	while (true) {
 		bool changed = false;
 		// forward then backward sweep over my weak pixels (Gauss-Seidel inside the segment)
