@@ -27,6 +27,9 @@ FAST_SET_INT_FAST_TYPE = 4
 FAST_SET_BOOL_NON_MAXIMA_SUPP = 5
 FAST_TYPE_9 = 6
 FAST_TYPE_12 = 7
+EDGE_SET_BOOL_X86_SSE41_GMAX_LANES = 1000
+EDGE_SET_BOOL_GENERIC_KERNEL = 1001
+HOUGH_SET_BOOL_X86_SIMD_SCAN = 1002
 CANNY_ID = 20
 CANNY_SET_INT_KERNEL_SIZE = 21
 CANNY_SET_INT_THRESHOLD_TYPE = 22
