@@ -307,4 +307,138 @@ static int launch_canny_fast_t(const FastParams& p0, size_t batch, cudaStream_t 
 	return CVB200_S_OK;
 }
 
+// ---- Sobel detector (edge_dete.cxx:55-206) on the same staged tile: pass 1 (MODE 2) = per-frame maximum of g = |gx| + |gy|, pass 2 (MODE 3) = u8(trunc(g * 255.f / gmax)).
+// Same arithmetic as edge_front_kernel<3, 2|3> in edges.cu; 4 pixels per lane, no intermediate tile: the gradient never leaves the registers.
+template <int MODE>
+__global__ void __launch_bounds__(CF_THREADS, 3)
+sobel_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams p, unsigned int* __restrict__ gmaxOut, const unsigned int* __restrict__ gmaxIn, int gmaxLanes)
+{
+	using G = CFGeom<0>;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const unsigned int pad = (128u - (static_cast<unsigned int>(__cvta_generic_to_shared(smem_raw)) & 127u)) & 127u;
+	unsigned int* base = reinterpret_cast<unsigned int*>(smem_raw + pad);
+	unsigned int* sA = base + 32;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(sA + (G::WORDS - G::OFF_A) + 2);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int W = p.W, H = p.H;
+	const int x0 = blockIdx.x * CF_TW, y0 = blockIdx.y * CF_TH;
+	const int frame = blockIdx.z;
+	const int xl = x0 - 4 + 4 * lane;
+	const int yIn0 = y0 - 2;                              // image row of staged row 0 (CFGeom<0>: rows y0-2 .. y0+TH+1)
+	const int xTma = (x0 - 4) & ~15;
+	const int woff = ((x0 - 4) - xTma) >> 2;
+	if (p.useTma) {
+		if (threadIdx.x == 0) {
+			mbar_init(bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			mbar_expect_tx(bar, G::IN_ROWS * CF_INW * 4);
+			tma_load_3d(sA, &tmap, bar, xTma, yIn0, frame);
+		}
+		__syncthreads();
+		mbar_wait(bar, 0);
+	}
+	else {
+		const uint8_t* __restrict__ in = p.in + frame * p.framePitch;
+		for (int r = warp; r < G::IN_ROWS; r += CF_WARPS) {
+			const int y = yIn0 + r;
+			unsigned int w = 0;
+			if (y >= 0 && y < H) {
+				const uint8_t* row = in + static_cast<size_t>(y) * p.stride;
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int x = xl + i;
+					if (x >= 0 && x < W) w |= static_cast<unsigned int>(row[x]) << (8 * i);
+				}
+			}
+			sA[r * CF_INW + woff + lane] = w;
+		}
+		__syncthreads();
+	}
+	constexpr int RPW = (CF_TH + CF_WARPS - 1) / CF_WARPS; // 8 output rows per warp
+	const int ro0 = warp * RPW;
+	int hs[3][4], hd[3][4]; // per source row: hs[i] = p[i-1] + 2p[i] + p[i+1], hd[i] = p[i+1] - p[i-1]
+	const unsigned int* src = sA + woff + lane;
+	auto loadRow = [&](int rb, int slot) {
+		const unsigned int* sw = src + rb * CF_INW;
+		const unsigned int wl = sw[-1], wc = sw[0], wr = sw[1];
+		int q[6];
+		q[0] = static_cast<int>(wl >> 24);
+		q[1] = static_cast<int>(wc & 0xff); q[2] = static_cast<int>((wc >> 8) & 0xff); q[3] = static_cast<int>((wc >> 16) & 0xff); q[4] = static_cast<int>(wc >> 24);
+		q[5] = static_cast<int>(wr & 0xff);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) { hs[slot][i] = q[i] + 2 * q[i + 1] + q[i + 2]; hd[slot][i] = q[i + 2] - q[i]; }
+	};
+	const bool laneOut = (lane >= 1 && lane <= 30);
+	unsigned int localMax = 0;
+	float scale = 0.f;
+	if (MODE == 3) scale = __fdiv_rn(255.f, static_cast<float>(max(gmaxIn[frame], 1u))); // scaleAndClip (compv_math_utils.cxx:336-364)
+	uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
+	// output row y0 + ro reads staged rows ro + 1, ro + 2, ro + 3 (image rows y-1, y, y+1)
+	loadRow(ro0 + 1, 0);
+	loadRow(ro0 + 2, 1);
+#pragma unroll
+	for (int j = 0; j < RPW; ++j) {
+		const int ro = ro0 + j;
+		if (ro < CF_TH) { // warp-uniform
+			loadRow(ro + 3, (j + 2) % 3);
+			const int a = j % 3, b = (j + 1) % 3, c = (j + 2) % 3;
+			const int y = y0 + ro;
+			const bool rowOk = (y >= 1 && y < H - 1);
+			unsigned int outw = 0;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int x = xl + i;
+				int gx = hd[a][i] + 2 * hd[b][i] + hd[c][i];
+				int gy = hs[c][i] - hs[a][i];
+				if (!(rowOk && x >= 1 && x < W - 1)) { gx = 0; gy = 0; } // the r = 1 border ring of the convolutions is zero
+				const unsigned int g = static_cast<unsigned int>(abs(gx) + abs(gy));
+				if (MODE == 2) {
+					if (laneOut && x < W && y < H && (!gmaxLanes || ((0x17u >> (x & 7)) & 1u))) localMax = max(localMax, g);
+				}
+				else {
+					const int v = __float2int_rz(__fmul_rn(static_cast<float>(g), scale));
+					outw |= static_cast<unsigned int>(min(max(v, 0), 255)) << (8 * i);
+				}
+			}
+			if (MODE == 3 && laneOut && y < H && xl < W) {
+				uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
+				if (p.vecStore && xl + 4 <= W) *reinterpret_cast<unsigned int*>(o) = outw;
+				else {
+#pragma unroll
+					for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+				}
+			}
+		}
+	}
+	if (MODE == 2) {
+		for (int o = 16; o; o >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
+		if (lane == 0 && localMax) atomicMax(&gmaxOut[frame], localMax);
+	}
+}
+
+static int launch_sobel_fast(const FastParams& p0, unsigned int* gmax, int gmaxLanes, size_t batch, cudaStream_t stream)
+{
+	using G = CFGeom<0>;
+	FastParams p = p0;
+	alignas(64) CUtensorMap map;
+	memset(&map, 0, sizeof(map));
+	p.useTma = make_u8_tile_map(&map, p.in, p.W, p.H, p.stride, p.framePitch, batch, CF_INW * 4, G::IN_ROWS) ? 1 : 0;
+	p.vecStore = (((reinterpret_cast<uintptr_t>(p.cls) | p.stride | p.framePitch) & 3) == 0) ? 1 : 0;
+	static bool attrSet = false;
+	if (!attrSet) {
+		CVB_CUDA(cudaFuncSetAttribute(sobel_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)));
+		CVB_CUDA(cudaFuncSetAttribute(sobel_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)));
+		attrSet = true;
+	}
+	dim3 grid(static_cast<unsigned>(div_up(p.W, CF_TW)), static_cast<unsigned>(div_up(p.H, CF_TH)), static_cast<unsigned>(batch));
+	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
+	{ KernelScope ks_("edge_gmax", stream);
+	  sobel_fast_kernel<2><<<grid, CF_THREADS, G::SMEM, stream>>>(map, p, gmax, nullptr, gmaxLanes); }
+	CVB_LAUNCHED();
+	{ KernelScope ks_("edge_normalize", stream);
+	  sobel_fast_kernel<3><<<grid, CF_THREADS, G::SMEM, stream>>>(map, p, nullptr, gmax, gmaxLanes); }
+	CVB_LAUNCHED();
+	return CVB200_S_OK;
+}
+
 } // namespace cvb

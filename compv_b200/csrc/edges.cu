@@ -615,6 +615,12 @@ int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, si
 		unsigned int* gmax = d->counters.as<unsigned int>();
 		// `uint16_t gmax = 1` (edge_dete.cxx:93) then max over the frame: the normalisation pass uses max(gmax, 1)
 		CVB_CUDA(cudaMemsetAsync(gmax, 0, batch * sizeof(unsigned int), stream));
+		if (d->id == CVB200_SOBEL_ID && d->taps.ks == 3 && !d->genericKernel) { // fast path (canny_fast.cuh): TMA-staged tile, 4 px per lane, both passes
+			FastParams f;
+			memset(&f, 0, sizeof(f));
+			f.in = image; f.cls = edges; f.W = p.W; f.H = p.H; f.stride = stride; f.framePitch = framePitch;
+			return launch_sobel_fast(f, gmax, d->gmaxLanes ? 1 : 0, batch, stream);
+		}
 		p.gmax = gmax;
 		p.gmaxLanes = d->gmaxLanes ? 1 : 0;
 		CVB_CHECK(launch_front(p, 2, batch, stream));
