@@ -100,8 +100,9 @@ static int morph_launch(const uint8_t* in, uint8_t* out, const short2* dTaps, co
 	return CVB200_S_OK;
 }
 
-static std::mutex g_morph_mutex;
+static std::mutex g_morph_mutex, g_morph_host_mutex;
 static DevBuf g_morph_taps, g_morph_tmp, g_morph_in, g_morph_out;
+static cudaEvent_t g_morph_done = nullptr; // the tap list and the open/close intermediate are shared scratch: a call waits for the previous one, whatever its stream
 
 } // namespace cvb
 
@@ -160,6 +161,9 @@ int cvb200_morph_process_dev(const uint8_t* in, size_t width, size_t height, siz
 	p.border = borderType;
 	p.nTaps = (taps.size() == strelWidth * strelHeight) ? 0 : static_cast<int>(taps.size());
 	std::lock_guard<std::mutex> lock(g_morph_mutex);
+	if (!g_morph_done) CVB_CUDA(cudaEventCreateWithFlags(&g_morph_done, cudaEventDisableTiming));
+	else CVB_CUDA(cudaStreamWaitEvent(stream, g_morph_done, 0));
+	struct Done { cudaStream_t s; ~Done() { cudaEventRecord(g_morph_done, s); } } done_{ stream };
 	CVB_CHECK(g_morph_taps.ensure(taps.size() * sizeof(short2)));
 	CVB_CUDA(cudaMemcpyAsync(g_morph_taps.p, taps.data(), taps.size() * sizeof(short2), cudaMemcpyHostToDevice, stream));
 	const short2* dTaps = g_morph_taps.as<short2>();
@@ -180,11 +184,9 @@ int cvb200_morph_process(const uint8_t* in, size_t width, size_t height, size_t 
 	CVB_REQUIRE_INIT();
 	CVB_REQUIRE(in && out && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
 	const size_t n = stride * height;
-	{
-		std::lock_guard<std::mutex> lock(g_morph_mutex);
-		CVB_CHECK(g_morph_in.ensure(n));
-		CVB_CHECK(g_morph_out.ensure(n));
-	}
+	std::lock_guard<std::mutex> hostLock(g_morph_host_mutex); // the staging buffers are shared: one host-buffer call at a time
+	CVB_CHECK(g_morph_in.ensure(n));
+	CVB_CHECK(g_morph_out.ensure(n));
 	CVB_CUDA(cudaMemcpyAsync(g_morph_in.p, in, n, cudaMemcpyHostToDevice, 0));
 	CVB_CUDA(cudaMemcpyAsync(g_morph_out.p, out, n, cudaMemcpyHostToDevice, 0)); // IGNORE keeps the caller's border cells
 	CVB_CHECK(cvb200_morph_process_dev(g_morph_in.as<uint8_t>(), width, height, stride, strel, strelWidth, strelHeight, strelStride, g_morph_out.as<uint8_t>(), opType, borderType, 1, n, nullptr));
