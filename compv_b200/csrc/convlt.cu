@@ -8,6 +8,7 @@
 // HBM traffic = 1 read of the input (+ halo re-reads that hit L2) + 1 write of the output; the intermediate plane of the
 // CPU implementation (sizeof(Out) B/px written and re-read) never exists.
 #include "common.cuh"
+#include "convlt_fast.cuh"
 
 #include <type_traits>
 #include <cmath>
@@ -156,6 +157,13 @@ static int convlt1_launch(const In* in, size_t width, size_t height, size_t stri
 	Taps<K> taps;
 	memset(&taps, 0, sizeof(taps));
 	for (size_t i = 0; i < kernSize; ++i) { taps.vt[i] = vtKern[i]; taps.hz[i] = hzKern[i]; }
+	if constexpr (std::is_same<In, uint8_t>::value && std::is_same<K, float>::value && std::is_same<Out, uint8_t>::value && !FXP) {
+		// the Gaussian-blur case: TMA-staged tile, 4 px per lane (convlt_fast.cuh); frames the TMA unit cannot address fall through to the generic kernel
+		int rc = 1;
+		if (kernSize == 3) rc = launch_convlt_fast<3>(in, out, width, height, stride, framePitch, vtKern, hzKern, borderType, batch, stream);
+		else if (kernSize == 5) rc = launch_convlt_fast<5>(in, out, width, height, stride, framePitch, vtKern, hzKern, borderType, batch, stream);
+		if (rc != 1) return rc;
+	}
 	const int r = static_cast<int>(kernSize >> 1);
 	const size_t tw = CONV_TW + 2 * r, th = CONV_TH + 2 * r;
 	const size_t smem = ((tw * th * sizeof(In) + 15) & ~static_cast<size_t>(15)) + CONV_TW * th * sizeof(Out);
