@@ -45,7 +45,7 @@ def test_convlt1_zero_border(cvb, name, ks, w, h, stride):
     _same(cvb.convlt1(name, img, vt, hz, width=w), oracle.convlt1("orc", name, img, vt, hz, width=w), w)
 
 
-@pytest.mark.parametrize("name", ["8u16s16s", "8u32f32f", "fxp_8u16u8u"])
+@pytest.mark.parametrize("name", ["8u16s16s", "8u32f32f", "8u32f8u", "fxp_8u16u8u"])
 @pytest.mark.parametrize("border", [1, 2])
 def test_convlt1_other_borders(cvb, name, border):
     tin, tk, tout = oracle.CONV_TYPES[name]
@@ -76,3 +76,19 @@ def test_gauss_kernels(cvb):
     for size, sigma in [(3, 0.8), (5, 1.0), (7, 2.0), (9, 1.7)]:
         np.testing.assert_array_equal(cvb.gauss_kernel(size, sigma).view(np.uint32), oracle.gauss_kernel("orc", size, sigma).view(np.uint32))
         np.testing.assert_array_equal(cvb.gauss_kernel(size, sigma, True), oracle.gauss_kernel("orc", size, sigma, True))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ks", [3, 5])
+@pytest.mark.parametrize("border", [0, 1, 2])
+@pytest.mark.parametrize("w,h,stride", [(120, 60, 128), (121, 61, 128), (240, 119, 240), (250, 125, 256), (7, 9, 16), (333, 77, 384)])
+def test_convlt1_8u32f8u_tma_path(cvb, ks, border, w, h, stride):
+    """16-byte aligned strides take the TMA-staged 4-px-per-lane kernel: every border type, tile edges, negative taps (clamping), tiny frames."""
+    rng = np.random.default_rng(ks * 100 + border * 10 + w)
+    img = frame_uniform(w, h, int(rng.integers(1 << 30)), stride)
+    vt = (rng.random(ks).astype(np.float32) - np.float32(0.3))
+    hz = oracle.gauss_kernel("orc", ks, 1.0)
+    base = rng.integers(0, 100, (h, stride)).astype(np.uint8)
+    a = cvb.convlt1("8u32f8u", img, vt, hz, width=w, border=border, out=base.copy())
+    b = oracle.convlt1("orc", "8u32f8u", img, vt, hz, width=w, border=border, out=base.copy())
+    np.testing.assert_array_equal(a[:, :w], b[:, :w])
