@@ -7,6 +7,7 @@
 //   adaptive   : fused kernel -- tile in shared memory, fixed-point horizontal then vertical mean (u8 intermediate, exactly K3 of convlt.cu),
 //                then out = (in - mean > -delta) ? maxVal : 0 (the reference's 768-entry LUT)    HBM: 1 B/px read + 1 B/px written
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <cstring>
 
@@ -159,6 +160,122 @@ threshold_adaptive_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ 
 	}
 }
 
+// ---- adaptive threshold, fast path: TMA-staged tile, 4 px per lane (same structure as convlt_fast.cuh), block sizes 3 / 5 / 7 ----
+constexpr int AF_TW = 120, AF_TH = 60, AF_THREADS = 256, AF_WARPS = 8, AF_ROWW = 32, AF_INW = 36;
+
+template <int KS>
+__global__ void __launch_bounds__(AF_THREADS, 3)
+threshold_adaptive_fast_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ outAll, int W, int H, size_t stride, size_t framePitch, const AdaptTaps taps,
+	int deltaInt, int maxVal, int invert, int vecStore)
+{
+	constexpr int R = KS >> 1;
+	constexpr int IN_ROWS = AF_TH + 2 * R;
+	extern __shared__ __align__(128) unsigned char af_smem[];
+	const unsigned int pad = (128u - (static_cast<unsigned int>(__cvta_generic_to_shared(af_smem)) & 127u)) & 127u;
+	unsigned int* sA = reinterpret_cast<unsigned int*>(af_smem + pad);
+	unsigned int* sM = sA + IN_ROWS * AF_INW + 4;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(sM + IN_ROWS * AF_ROWW + 2);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int x0 = blockIdx.x * AF_TW, y0 = blockIdx.y * AF_TH, frame = blockIdx.z;
+	const int xl = x0 - 4 + 4 * lane;
+	const int yIn0 = y0 - R;
+	const int xTma = (x0 - 4) & ~15;
+	const int woff = ((x0 - 4) - xTma) >> 2;
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_expect_tx(bar, IN_ROWS * AF_INW * 4);
+		tma_load_3d(sA, &tmap, bar, xTma, yIn0, frame);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+	unsigned int hz[KS], vt[KS];
+#pragma unroll
+	for (int k = 0; k < KS; ++k) { hz[k] = taps.hz[k]; vt[k] = taps.vt[k]; }
+	// horizontal fixed-point mean (compv_math_convlt.h:386-405), zero on the R-wide column border
+	unsigned int convMask = 0;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) if (xl + i >= R && xl + i < W - R) convMask |= 0xffu << (8 * i);
+	for (int r = warp; r < IN_ROWS; r += AF_WARPS) {
+		const int y = yIn0 + r;
+		unsigned int outw = 0;
+		if (y >= 0 && y < H && convMask) {
+			const unsigned int* q = &sA[r * AF_INW + woff + lane];
+			const unsigned int wl = q[-1], wc = q[0], wr = q[1];
+			unsigned int v[4 + 2 * R];
+#pragma unroll
+			for (int j = 0; j < R; ++j) v[j] = (wl >> (8 * (4 - R + j))) & 0xffu;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) v[R + j] = (wc >> (8 * j)) & 0xffu;
+#pragma unroll
+			for (int j = 0; j < R; ++j) v[R + 4 + j] = (wr >> (8 * j)) & 0xffu;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				unsigned int sum = 0;
+#pragma unroll
+				for (int k = 0; k < KS; ++k) sum += (v[i + k] * hz[k]) >> 16;
+				outw |= min(sum, 255u) << (8 * i);
+			}
+			outw &= convMask;
+		}
+		sM[r * AF_ROWW + lane] = outw;
+	}
+	__syncthreads();
+	// vertical pass (zero on the R-high row border) + LUT compare: lut[in - mean + 255], first (255 - delta + 1) entries "off" (compv_image_threshold.cxx:221-225, 283-286)
+	const unsigned int onVal = invert ? 0u : static_cast<unsigned int>(maxVal), offVal = invert ? static_cast<unsigned int>(maxVal) : 0u;
+	const int cut = 255 - deltaInt + 1;
+	constexpr int RPW = (AF_TH + AF_WARPS - 1) / AF_WARPS;
+	const int ro0 = warp * RPW;
+	const bool laneOut = (lane >= 1 && lane <= 30) && xl < W;
+	uint8_t* __restrict__ out = outAll + frame * framePitch;
+#pragma unroll 1
+	for (int j = 0; j < RPW; ++j) {
+		const int ro = ro0 + j;
+		const int y = y0 + ro;
+		if (ro >= AF_TH || y >= H || !laneOut) continue;
+		unsigned int mean[4] = { 0, 0, 0, 0 };
+		if (y >= R && y < H - R) {
+#pragma unroll
+			for (int k = 0; k < KS; ++k) {
+				const unsigned int w = sM[(ro + k) * AF_ROWW + lane];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) mean[i] += (((w >> (8 * i)) & 0xffu) * vt[k]) >> 16;
+			}
+		}
+		const unsigned int wc = sA[(ro + R) * AF_INW + woff + lane];
+		unsigned int outw = 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const int idx = static_cast<int>((wc >> (8 * i)) & 0xffu) - static_cast<int>(min(mean[i], 255u)) + 255;
+			outw |= (idx >= cut ? onVal : offVal) << (8 * i);
+		}
+		uint8_t* o8 = out + static_cast<size_t>(y) * stride + xl;
+		if (vecStore && xl + 4 <= W) *reinterpret_cast<unsigned int*>(o8) = outw;
+		else {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) if (xl + i < W) o8[i] = static_cast<uint8_t>(outw >> (8 * i));
+		}
+	}
+}
+
+template <int KS>
+static int adaptive_fast_launch(const uint8_t* in, uint8_t* out, size_t W, size_t H, size_t stride, size_t framePitch, const AdaptTaps& taps, int deltaInt, int maxVal, int invert,
+	size_t batch, cudaStream_t stream)
+{
+	constexpr int IN_ROWS = AF_TH + 2 * (KS >> 1);
+	alignas(64) CUtensorMap map;
+	memset(&map, 0, sizeof(map));
+	if (!make_u8_tile_map(&map, in, W, H, stride, framePitch, batch, AF_INW * 4, IN_ROWS)) return 1; // not addressable by the TMA unit: the caller takes the generic kernel
+	const size_t smem = (static_cast<size_t>(IN_ROWS) * (AF_INW + AF_ROWW) + 8) * 4 + 128 + 16;
+	dim3 grid(static_cast<unsigned>(div_up(W, AF_TW)), static_cast<unsigned>(div_up(H, AF_TH)), static_cast<unsigned>(batch));
+	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
+	const int vecStore = (((reinterpret_cast<uintptr_t>(out) | stride | framePitch) & 3) == 0) ? 1 : 0;
+	{ KernelScope ks_("threshold_adaptive", stream);
+	  threshold_adaptive_fast_kernel<KS><<<grid, AF_THREADS, smem, stream>>>(map, out, static_cast<int>(W), static_cast<int>(H), stride, framePitch, taps, deltaInt, maxVal, invert, vecStore); }
+	CVB_LAUNCHED();
+	return CVB200_S_OK;
+}
+
 static int launch_histogram(const uint8_t* in, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, unsigned int* hist, cudaStream_t stream)
 {
 	CVB_CUDA(cudaMemsetAsync(hist, 0, batch * 256 * sizeof(unsigned int), stream));
@@ -256,6 +373,14 @@ static int adaptive_launch(const uint8_t* in, size_t width, size_t height, size_
 	const int r = static_cast<int>(kernSize >> 1);
 	const size_t tw = AD_TW + 2 * r, th = AD_TH + 2 * r;
 	const size_t smem = ((tw * th + 15) & ~static_cast<size_t>(15)) + AD_TW * th;
+	{
+		const size_t fp = framePitch ? framePitch : stride * height;
+		int rc = 1;
+		if (kernSize == 3) rc = adaptive_fast_launch<3>(in, out, width, height, stride, fp, taps, deltaInt, maxValU8, invert ? 1 : 0, batch, stream);
+		else if (kernSize == 5) rc = adaptive_fast_launch<5>(in, out, width, height, stride, fp, taps, deltaInt, maxValU8, invert ? 1 : 0, batch, stream);
+		else if (kernSize == 7) rc = adaptive_fast_launch<7>(in, out, width, height, stride, fp, taps, deltaInt, maxValU8, invert ? 1 : 0, batch, stream);
+		if (rc != 1) return rc;
+	}
 	auto kern = threshold_adaptive_kernel<0>;
 	if (kernSize == 3) kern = threshold_adaptive_kernel<3>;
 	else if (kernSize == 5) kern = threshold_adaptive_kernel<5>;

@@ -59,3 +59,15 @@ def test_cuda_threshold_errors(cvb):
     with pytest.raises(_ffi.CvbError) as e:
         cvb.threshold_adaptive(img, block_size=4)            # even block size (compv_image_threshold.cxx:185)
     assert e.value.code == _ffi.E_INVALID_PARAMETER
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [3, 5, 7])
+@pytest.mark.parametrize("w,h,stride", [(120, 60, 128), (121, 61, 128), (240, 119, 240), (250, 125, 256), (9, 11, 16), (640, 360, 640)])
+def test_cuda_adaptive_tma_path(cvb, bs, w, h, stride):
+    """16-byte aligned strides take the TMA-staged kernel: block sizes 3/5/7, tile edges, tiny frames, both polarities, padding bytes ignored."""
+    from frames import frame_uniform, frame_text
+    img = frame_uniform(w, h, bs * 7 + w, stride) if w % 2 else np.ascontiguousarray(np.pad(frame_text(w, h, bs), ((0, 0), (0, stride - w)), constant_values=33))
+    for delta, mv, inv in [(8.0, 255.0, False), (0.0, 200.0, True), (40.5, 255.0, False)]:
+        np.testing.assert_array_equal(cvb.threshold_adaptive(img, bs, delta, mv, inv, width=w)[:, :w],
+                                      oracle.threshold("orc", "adaptive", img, block_size=bs, delta=delta, max_val=mv, invert=inv, width=w)[0][:, :w])
