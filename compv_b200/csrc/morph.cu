@@ -6,6 +6,7 @@
 // separably -- running min / max along rows into a second tile, then along columns: sw + sh operations per pixel instead of sw * sh --, any other element
 // walks the list of its non-zero cells.  The reference's border rule is applied in the same kernel, so a basic operation reads the frame once and writes it once.
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <cstring>
 #include <vector>
@@ -85,8 +86,123 @@ __global__ void __launch_bounds__(MORPH_THREADS) morph_basic_kernel(const uint8_
 	}
 }
 
+// ---- fast path: full rectangles of 3 or 5 rows / columns (the elements the text pipeline uses) ----
+// Same staging as convlt_fast.cuh (one TMA bulk-tensor copy per CTA, 4 pixels per lane); min / max are byte-wise SIMD-in-a-word (__vminu4 / __vmaxu4) on the packed
+// pixels: the horizontal neighbours of a word are two byte permutes of it and its neighbours, so a 3x3 basic operation costs about a dozen instructions per 4 pixels.
+constexpr int MF_TW = 120, MF_TH = 60, MF_THREADS = 256, MF_WARPS = 8, MF_ROWW = 32, MF_INW = 36;
+
+template <bool ERODE> __device__ __forceinline__ unsigned int morph_op4(unsigned int a, unsigned int b) { return ERODE ? __vminu4(a, b) : __vmaxu4(a, b); }
+
+template <bool ERODE, int SW, int SH>
+__global__ void __launch_bounds__(MF_THREADS, 3)
+morph_rect_fast_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ outAll, int W, int H, size_t stride, size_t framePitch, int border, int vecStore)
+{
+	constexpr int RW = SW >> 1, RH = SH >> 1, BH = (SH + 1) >> 1;
+	constexpr int IN_ROWS = MF_TH + 2 * RH;
+	extern __shared__ __align__(128) unsigned char mf_smem[];
+	const unsigned int pad = (128u - (static_cast<unsigned int>(__cvta_generic_to_shared(mf_smem)) & 127u)) & 127u;
+	unsigned int* sA = reinterpret_cast<unsigned int*>(mf_smem + pad);
+	unsigned int* sM = sA + IN_ROWS * MF_INW + 4;
+	uint64_t* bar = reinterpret_cast<uint64_t*>(sM + IN_ROWS * MF_ROWW + 2);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int x0 = blockIdx.x * MF_TW, y0 = blockIdx.y * MF_TH, frame = blockIdx.z;
+	const int xl = x0 - 4 + 4 * lane;
+	const int yIn0 = y0 - RH;
+	const int xTma = (x0 - 4) & ~15;
+	const int woff = ((x0 - 4) - xTma) >> 2;
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_expect_tx(bar, IN_ROWS * MF_INW * 4);
+		tma_load_3d(sA, &tmap, bar, xTma, yIn0, frame);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+	// rows: for each of my 4 pixels the min / max over columns x-RW .. x+RW (bytes shifted in from the neighbouring words)
+	for (int r = warp; r < IN_ROWS; r += MF_WARPS) {
+		const unsigned int* q = &sA[r * MF_INW + woff + lane];
+		const unsigned int wl = q[-1], wc = q[0], wr = q[1];
+		unsigned int v = wc;
+		v = morph_op4<ERODE>(v, __byte_perm(wl, wc, 0x6543)); // x-1
+		v = morph_op4<ERODE>(v, __byte_perm(wc, wr, 0x4321)); // x+1
+		if (RW == 2) {
+			v = morph_op4<ERODE>(v, __byte_perm(wl, wc, 0x5432)); // x-2
+			v = morph_op4<ERODE>(v, __byte_perm(wc, wr, 0x5432)); // x+2
+		}
+		sM[r * MF_ROWW + lane] = v;
+	}
+	__syncthreads();
+	unsigned int inImage = 0, colBand = 0;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		if (xl + i < W) inImage |= 0xffu << (8 * i);
+		if (xl + i < RW || xl + i >= W - RW) colBand |= 0xffu << (8 * i);
+	}
+	const bool laneOut = (lane >= 1 && lane <= 30) && xl < W;
+	uint8_t* __restrict__ out = outAll + frame * framePitch;
+	for (int ro = warp; ro < MF_TH; ro += MF_WARPS) {
+		const int y = y0 + ro;
+		if (y >= H) break; // warp-uniform
+		if (!laneOut) continue;
+		unsigned int v = sM[ro * MF_ROWW + lane];
+#pragma unroll
+		for (int k = 1; k < SH; ++k) v = morph_op4<ERODE>(v, sM[(ro + k) * MF_ROWW + lane]);
+		const bool rowComputed = (y >= RH && y < H - RH), rowBand = (y < BH || y >= H - BH);
+		// the reference computes the interior, then overwrites the border rows (addBordersVt), then the border columns (addBordersHz)
+		const unsigned int band = rowBand ? 0xffffffffu : colBand;
+		const unsigned int computed = rowComputed ? ~colBand : 0u;
+		unsigned int value, storeMask;
+		if (border == CVB200_BORDER_TYPE_IGNORE) { value = v; storeMask = computed & inImage; }
+		else {
+			const unsigned int b = (border == CVB200_BORDER_TYPE_ZERO) ? 0u : sA[(ro + RH) * MF_INW + woff + lane];
+			value = (b & band) | (v & ~band);
+			storeMask = inImage;
+		}
+		if (!storeMask) continue;
+		uint8_t* o8 = out + static_cast<size_t>(y) * stride + xl;
+		if (vecStore && storeMask == 0xffffffffu) *reinterpret_cast<unsigned int*>(o8) = value;
+		else {
+#pragma unroll
+			for (int i = 0; i < 4; ++i) if ((storeMask >> (8 * i)) & 0xffu) o8[i] = static_cast<uint8_t>(value >> (8 * i));
+		}
+	}
+}
+
+// CVB200_S_OK when the fast path ran, 1 when it does not apply (element, alignment): the caller takes the generic kernel
+template <bool ERODE, int SW, int SH>
+static int morph_rect_fast_launch_t(const uint8_t* in, uint8_t* out, const MorphParams& p, size_t batch, cudaStream_t stream)
+{
+	constexpr int IN_ROWS = MF_TH + 2 * (SH >> 1);
+	alignas(64) CUtensorMap map;
+	memset(&map, 0, sizeof(map));
+	if (!make_u8_tile_map(&map, in, p.W, p.H, p.stride, p.framePitch, batch, MF_INW * 4, IN_ROWS)) return 1;
+	const size_t smem = (static_cast<size_t>(IN_ROWS) * (MF_INW + MF_ROWW) + 8) * 4 + 128 + 16;
+	dim3 grid(static_cast<unsigned>(div_up(p.W, MF_TW)), static_cast<unsigned>(div_up(p.H, MF_TH)), static_cast<unsigned>(batch));
+	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
+	const int vecStore = (((reinterpret_cast<uintptr_t>(out) | p.stride | p.framePitch) & 3) == 0) ? 1 : 0;
+	{ KernelScope ks_(ERODE ? "morph_erode" : "morph_dilate", stream);
+	  morph_rect_fast_kernel<ERODE, SW, SH><<<grid, MF_THREADS, smem, stream>>>(map, out, p.W, p.H, p.stride, p.framePitch, p.border, vecStore); }
+	CVB_LAUNCHED();
+	return CVB200_S_OK;
+}
+
+template <bool ERODE>
+static int morph_rect_fast_launch(const uint8_t* in, uint8_t* out, const MorphParams& p, size_t batch, cudaStream_t stream)
+{
+	if (p.nTaps != 0) return 1;
+	if (p.sw == 3 && p.sh == 3) return morph_rect_fast_launch_t<ERODE, 3, 3>(in, out, p, batch, stream);
+	if (p.sw == 5 && p.sh == 5) return morph_rect_fast_launch_t<ERODE, 5, 5>(in, out, p, batch, stream);
+	if (p.sw == 3 && p.sh == 5) return morph_rect_fast_launch_t<ERODE, 3, 5>(in, out, p, batch, stream);
+	if (p.sw == 5 && p.sh == 3) return morph_rect_fast_launch_t<ERODE, 5, 3>(in, out, p, batch, stream);
+	return 1;
+}
+
 static int morph_launch(const uint8_t* in, uint8_t* out, const short2* dTaps, const MorphParams& p, bool erode, size_t batch, cudaStream_t stream)
 {
+	{
+		const int rc = erode ? morph_rect_fast_launch<true>(in, out, p, batch, stream) : morph_rect_fast_launch<false>(in, out, p, batch, stream);
+		if (rc != 1) return rc;
+	}
 	const size_t tw = MORPH_TW + p.sw - 1, th = MORPH_TH + p.sh - 1;
 	const size_t smem = ((tw * th + 15) & ~static_cast<size_t>(15)) + MORPH_TW * th;
 	CVB_REQUIRE(smem <= 200 * 1024, CVB200_E_OUT_OF_BOUND);
