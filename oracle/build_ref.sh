@@ -40,3 +40,13 @@ if [ -f "$HERE/ref_shim.cxx" ]; then
      "$HERE/ref_shim.cxx" -o "$OUT/libcompv_refshim.so" -L"$OUT" -lcompv_ref -ldl -lpthread -Wl,-rpath,'$ORIGIN'
   echo "[build_ref] linked $OUT/libcompv_refshim.so"
 fi
+
+# The real CompVFeature::addFactory adapter (integration/compv_b200_plugin.cxx): needs the reference headers AND the built product library
+PLUGIN_SRC="$HERE/../integration/compv_b200_plugin.cxx"
+B200_LIB="$HERE/../compv_b200/lib"
+if [ -f "$PLUGIN_SRC" ] && [ -f "$B200_LIB/libcompv_b200.so" ]; then
+  g++ -std=c++11 -O2 -fPIC -shared -w -include limits -include cstdint -include cmath -DCOMPV_ASM=0 $INC -I"$HERE/../include" \
+     "$PLUGIN_SRC" -o "$OUT/libcompv_b200_plugin.so" -L"$OUT" -lcompv_ref -L"$B200_LIB" -lcompv_b200 -ldl -lpthread \
+     -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../compv_b200/lib'
+  echo "[build_ref] linked $OUT/libcompv_b200_plugin.so"
+fi
