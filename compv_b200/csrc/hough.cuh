@@ -11,7 +11,7 @@ struct cvb200_hough {
 	bool x86Simd;
 	double lastGs;
 	// KHT scratch (hough_kht.cu)
-	cvb::DevBuf bits, poss, strings, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
+	cvb::DevBuf bits, poss, strings, strRev, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
 	cvb::HostBuf hFrames, hVotes, hCounts;
 	// SHT scratch (hough_sht.cu)
 	cvb::DevBuf shtTables, shtList, shtCursor, shtMask, shtPool, shtDesc;

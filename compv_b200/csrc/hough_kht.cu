@@ -16,6 +16,7 @@
 //   kht_scan / kht_kernels / kht_hmax / kht_gmin / kht_vote (one thread per kernel quadrant, integer atomicAdd) / kht_peaks (+ rank prefix)
 // Host: the thresholded, smoothed cells (a few thousand per frame) are sorted with the same libstdc++ std::sort as the reference and swept.
 #include "hough.cuh"
+#include "kht_walk.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -52,6 +53,7 @@ struct KhtFrame {           // per-frame offsets into the batch-wide pools + dev
 struct KhtStack { unsigned int a, b, mi, nclus0; double ratio, ratioLeft; unsigned int state, pad; };
 
 // ---- bitmap -------------------------------------------------------------------------------------
+template <bool REV>
 __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int* __restrict__ bits, KhtGeom g, unsigned int* edgeCount)
 {
 	const int frame = blockIdx.z, y = blockIdx.y;
@@ -72,7 +74,7 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 		else {
 			for (int j = 0; j < 32 && x0 + j < g.W; ++j) if (row[x0 + j]) word |= 1u << j;
 		}
-		bits[(static_cast<size_t>(frame) * (g.H + 2) + y + 1) * g.WW + wi + 1] = word;
+		bits[(static_cast<size_t>(frame) * (g.H + 2 * KHT_PADR) + y + KHT_PADR) * g.WW + wi + 1] = REV ? __brev(word) : word;
 	}
 	unsigned int c = __popc(word);
 	for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -141,11 +143,11 @@ __device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* bits, in
 }
 
 __global__ void __launch_bounds__(32)
-kht_link_kernel(unsigned int* bitsAll /* read and written through several derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
+kht_link_old_kernel(unsigned int* bitsAll /* read and written through several derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
 {
 	const int frame = blockIdx.x, lane = threadIdx.x;
 	const int W = g.W, H = g.H, WW = g.WW;
-	unsigned int* bits = bitsAll + (static_cast<size_t>(frame) * (H + 2) + 1) * WW; // padded row 0 of the frame
+	unsigned int* bits = bitsAll + (static_cast<size_t>(frame) * (H + 2 * KHT_PADR) + KHT_PADR) * WW; // padded word 0 of image row 0
 	KhtFrame& fr = frames[frame];
 	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff); // ushort2 {x, y} written as x | y << 16
 	uint2* strings = stringsAll + fr.strOff;
@@ -155,7 +157,7 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through several derive
 	// The seed scan reads rows in order, so rows above the scan line are in this SM's L1; walks mostly head DOWN into rows nobody has read yet and
 	// would pay an L2 round trip per new row (the chain's dominant latency).  The idle lanes therefore keep KHT_AHEAD rows below the scan line prefetched.
 	const char* bytes0 = reinterpret_cast<const char*>(bits - WW);                       // padded row -1
-	const size_t bytesEnd = static_cast<size_t>(H + 2) * WW * 4;
+	const size_t bytesEnd = static_cast<size_t>(H + 3) * WW * 4;
 	for (size_t o = static_cast<size_t>(lane) * 128; o < bytesEnd && o < static_cast<size_t>(KHT_AHEAD + 2) * WW * 4; o += 32 * 128)
 		asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
 	for (int y = 1; y < H - 1; ++y) {
@@ -218,6 +220,81 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through several derive
 		}
 	}
 	if (lane == 0) { fr.nPos = nPos; fr.nStr = nStr; }
+}
+
+// ---- linking (new): see kht_walk.cuh for the walker ----------------------------------------------
+// One warp per frame: the 32 lanes find the next seed in raster order (32 bitmap words per ballot), lane 0 runs Algorithm 5 for it.  The first walk of a
+// string is stored in walk order; the reversal the reference applies (std::reverse, houghkht.cxx:752-755) is left to kht_reverse_kernel, which is parallel
+// over strings, instead of a load-after-store round trip through L2 between two walks.
+template <bool REV, bool BF>
+__global__ void __launch_bounds__(32)
+kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll,
+	unsigned int* __restrict__ revAll, KhtFrame* frames, KhtGeom g)
+{
+	const int frame = blockIdx.x, lane = threadIdx.x;
+	const int W = g.W, H = g.H, WW = g.WW;
+	unsigned int* base = bitsAll + (static_cast<size_t>(frame) * (H + 2 * KHT_PADR) + KHT_PADR) * WW; // padded word 0 of image row 0
+	KhtFrame& fr = frames[frame];
+	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff); // ushort2 {x, y} written as x | y << 16
+	uint2* strings = stringsAll + fr.strOff;
+	unsigned int* revs = revAll + fr.strOff;
+	unsigned int nPos = 0, nStr = 0; // meaningful on lane 0
+	const int lastWord = (W - 1) >> 5;
+
+	// The seed scan reads rows in order, so rows above the scan line are in this SM's L1; walks mostly head DOWN into rows nobody has read yet and
+	// would pay an L2 round trip per new row.  The idle lanes therefore keep KHT_AHEAD rows below the scan line prefetched.
+	const char* bytes0 = reinterpret_cast<const char*>(base - KHT_PADR * WW);
+	const size_t bytesEnd = static_cast<size_t>(H + 2 * KHT_PADR) * WW * 4;
+	for (size_t o = static_cast<size_t>(lane) * 128; o < bytesEnd && o < static_cast<size_t>(KHT_AHEAD + KHT_PADR + 1) * WW * 4; o += 32 * 128)
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
+	for (int y = 1; y < H - 1; ++y) {
+		const unsigned int* row = base + static_cast<size_t>(y) * WW + 1; // word 0 of the image row
+		{
+			const size_t o = static_cast<size_t>(y + KHT_PADR + KHT_AHEAD) * WW * 4 + static_cast<size_t>(lane) * 128; // row y + KHT_AHEAD, one 128-byte line per lane
+			if (o < bytesEnd && lane * 128 < WW * 4 + 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
+		}
+		for (int wb = 0; wb <= lastWord; wb += 32) {
+			while (true) {
+				const int wi = wb + lane;
+				unsigned int w = (wi <= lastWord) ? row[wi] : 0u; // plain load: served by this SM's L1, which the walker's stores keep current
+				// seeds are interior columns only: x in [1, W-2]
+				if (wi == 0) w &= ~kw_colbit<REV>(0);
+				if (wi == lastWord) w &= ~kw_colbit<REV>((W - 1) & 31);
+				const unsigned int any = __ballot_sync(0xffffffffu, w != 0);
+				if (!any) break;
+				const int src = __ffs(any) - 1;
+				const unsigned int sw = __shfl_sync(0xffffffffu, w, src);
+				if (lane == 0) {
+					const int xr = (wb + src) * 32 + kw_first_col<REV>(sw);
+					unsigned int rev;
+					const unsigned int n = kht_link_string<REV, BF>(base, WW, static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16), poss + nPos, &rev);
+					if (n >= g.minSize) {
+						strings[nStr] = make_uint2(nPos, nPos + n);
+						revs[nStr] = rev;
+						++nStr; nPos += n;
+					}
+				}
+				__syncwarp();
+			}
+		}
+	}
+	if (lane == 0) { fr.nPos = nPos; fr.nStr = nStr; }
+}
+
+// the first walk of every string is stored in walk order: reverse it (houghkht.cxx:752-755).  One warp per string.
+__global__ void kht_reverse_kernel(ushort2* __restrict__ possAll, const uint2* __restrict__ stringsAll, const unsigned int* __restrict__ revAll, const KhtFrame* frames)
+{
+	const int frame = blockIdx.y, lane = threadIdx.x & 31;
+	const KhtFrame& fr = frames[frame];
+	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff);
+	const unsigned int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+	for (unsigned int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < fr.nStr; s += warpsPerGrid) {
+		const unsigned int begin = stringsAll[fr.strOff + s].x, n = revAll[fr.strOff + s];
+		for (unsigned int i = lane; i < n / 2; i += 32) {
+			const unsigned int a = poss[begin + i], b = poss[begin + n - 1 - i];
+			poss[begin + i] = b; poss[begin + n - 1 - i] = a;
+		}
+	}
 }
 
 // ---- cluster subdivision (houghkht.cxx:774-832) -------------------------------------------------
@@ -639,8 +716,9 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	g.threshold = static_cast<int>(h->threshold);
 	g.x86Simd = h->x86Simd ? 1 : 0;
 
+	static const int linkVariant = getenv("CVB200_KHT_LINK") ? atoi(getenv("CVB200_KHT_LINK")) : 2; // TEMPORARY A/B switch: 0 = round-1 walker, 1 = window walker, 2 = window walker on bit-reversed words
 	// ---- phase 1: bitmap + edge counts ----
-	const size_t bitWords = static_cast<size_t>(g.H + 2) * g.WW;
+	const size_t bitWords = static_cast<size_t>(g.H + 2 * KHT_PADR) * g.WW;
 	CVB_CHECK(h->bits.ensure(batch * bitWords * 4));
 	CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream)); // the zero border rows / words the walker relies on
 	CVB_CHECK(h->edgeCount.ensure(batch * 4));
@@ -650,7 +728,8 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 		dim3 grid(static_cast<unsigned>(div_up(g.WW, 64)), static_cast<unsigned>(g.H), static_cast<unsigned>(batch));
 		CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 		KernelScope ks_("kht_bits", stream);
-		kht_bits_kernel<<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, h->edgeCount.as<unsigned int>());
+		if (linkVariant == 2 || linkVariant == 3) kht_bits_kernel<true><<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, h->edgeCount.as<unsigned int>());
+		else kht_bits_kernel<false><<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, h->edgeCount.as<unsigned int>());
 	}
 	CVB_LAUNCHED();
 	unsigned int* hCounts = h->hCounts.as<unsigned int>();
@@ -691,9 +770,24 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	KhtFrame* dFrames = h->frames.as<KhtFrame>();
 	const unsigned int B = static_cast<unsigned int>(batch);
 
-	{ KernelScope ks_("kht_link", stream);
-	  kht_link_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), dFrames, g); }
-	CVB_LAUNCHED();
+	CVB_CHECK(h->strRev.ensure((strTotal + 1) * 4));
+	if (linkVariant == 0) {
+		KernelScope ks_("kht_link", stream);
+		kht_link_old_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), dFrames, g);
+		CVB_LAUNCHED();
+	}
+	else {
+		{ KernelScope ks_("kht_link", stream);
+		  unsigned int* bp = h->bits.as<unsigned int>(); ushort2* pp = h->poss.as<ushort2>(); uint2* sp = h->strings.as<uint2>(); unsigned int* rp = h->strRev.as<unsigned int>();
+		  if (linkVariant == 1) kht_link_kernel<false, false><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g);
+		  else if (linkVariant == 2) kht_link_kernel<true, false><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g);
+		  else if (linkVariant == 3) kht_link_kernel<true, true><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g);
+		  else kht_link_kernel<false, true><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g); }
+		CVB_LAUNCHED();
+		{ KernelScope ks_("kht_reverse", stream);
+		  kht_reverse_kernel<<<dim3(8, B), 128, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames); }
+		CVB_LAUNCHED();
+	}
 	{ KernelScope ks_("kht_subdivide", stream);
 	  kht_subdivide_kernel<<<dim3(32, B), 64, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->clus.as<uint2>(), h->nClusStr.as<unsigned int>(), h->stack.as<KhtStack>(), dFrames, g); }
 	CVB_LAUNCHED();
@@ -797,7 +891,7 @@ int cvb200_hough_free(cvb200_hough_t** hough)
 {
 	if (hough && *hough) {
 		cvb200_hough* h = *hough;
-		DevBuf* bufs[] = { &h->bits, &h->poss, &h->strings, &h->clus, &h->clusOrd, &h->nClusStr, &h->stack, &h->kern, &h->acc, &h->rowCount, &h->votes, &h->frames, &h->edgeCount, &h->hostIn,
+		DevBuf* bufs[] = { &h->bits, &h->poss, &h->strings, &h->strRev, &h->clus, &h->clusOrd, &h->nClusStr, &h->stack, &h->kern, &h->acc, &h->rowCount, &h->votes, &h->frames, &h->edgeCount, &h->hostIn,
 			&h->shtTables, &h->shtList, &h->shtCursor, &h->shtMask, &h->shtPool, &h->shtDesc };
 		for (DevBuf* b : bufs) b->release();
 		h->hFrames.release(); h->hVotes.release(); h->hCounts.release();

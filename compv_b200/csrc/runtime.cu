@@ -244,6 +244,9 @@ int cvb200_stream_sync(cvb200_stream_t stream)
 // ---- host worker pool ----
 namespace cvb {
 namespace {
+// One job at a time (callMutex).  Every job names its participants explicitly: a worker takes part in job `generation` only if it was alive when the job
+// was published (its `seen` starts at the generation current at its creation, so a worker created while growing the pool never mistakes an older, finished
+// job for a new one), and the job's function pointer is cleared before host_parallel_for returns.
 struct HostPool {
 	std::vector<std::thread> workers;
 	std::mutex m;
@@ -253,8 +256,7 @@ struct HostPool {
 	size_t n = 0, generation = 0, active = 0;
 	bool stop = false;
 	std::mutex callMutex; // one parallel_for at a time
-	void run() {
-		size_t seen = 0;
+	void run(size_t seen) {
 		for (;;) {
 			const std::function<void(size_t)>* f;
 			size_t count;
@@ -264,7 +266,7 @@ struct HostPool {
 				if (stop) return;
 				seen = generation; f = fn; count = n;
 			}
-			for (size_t i; (i = next.fetch_add(1, std::memory_order_relaxed)) < count;) (*f)(i);
+			if (f) for (size_t i; (i = next.fetch_add(1, std::memory_order_relaxed)) < count;) (*f)(i);
 			{
 				std::lock_guard<std::mutex> lk(m);
 				if (--active == 0) cvDone.notify_all();
@@ -280,16 +282,22 @@ struct HostPool {
 HostPool& host_pool() { static HostPool p; return p; }
 } // namespace
 
+static size_t g_host_threads_cap = 0; // 0 = hardware_concurrency (capped at 128); cvb200_set_host_threads
+
 void host_parallel_for(size_t n, const std::function<void(size_t)>& fn)
 {
 	if (n == 0) return;
 	HostPool& p = host_pool();
-	size_t want = std::thread::hardware_concurrency();
+	size_t want = g_host_threads_cap ? g_host_threads_cap : std::thread::hardware_concurrency();
 	if (want > 128) want = 128;
 	if (want > n) want = n;
 	if (want <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
 	std::lock_guard<std::mutex> call(p.callMutex);
-	while (p.workers.size() + 1 < want) p.workers.emplace_back([&p] { p.run(); });
+	while (p.workers.size() + 1 < want) {
+		size_t gen;
+		{ std::lock_guard<std::mutex> lk(p.m); gen = p.generation; } // no job is in flight here (callMutex): a new worker must wait for the NEXT generation
+		p.workers.emplace_back([&p, gen] { p.run(gen); });
+	}
 	{
 		std::lock_guard<std::mutex> lk(p.m);
 		p.fn = &fn; p.n = n; p.next.store(0); p.active = p.workers.size(); ++p.generation;
@@ -298,5 +306,21 @@ void host_parallel_for(size_t n, const std::function<void(size_t)>& fn)
 	for (size_t i; (i = p.next.fetch_add(1, std::memory_order_relaxed)) < n;) fn(i);
 	std::unique_lock<std::mutex> lk(p.m);
 	p.cvDone.wait(lk, [&] { return p.active == 0; });
+	p.fn = nullptr; p.n = 0;
 }
 } // namespace cvb
+
+extern "C" int cvb200_set_host_threads(int n)
+{
+	CVB_REQUIRE(n >= 0, CVB200_E_INVALID_PARAMETER);
+	cvb::g_host_threads_cap = static_cast<size_t>(n);
+	return CVB200_S_OK;
+}
+
+// test hook: fn(i) = out[i] += 1 through the pool (tests/test_abi.py grows the pool between calls)
+extern "C" int cvb200_selftest_host_pool(size_t n, unsigned int* out)
+{
+	CVB_REQUIRE(out || !n, CVB200_E_INVALID_PARAMETER);
+	cvb::host_parallel_for(n, [&](size_t i) { out[i] += 1; });
+	return CVB200_S_OK;
+}

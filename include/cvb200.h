@@ -143,6 +143,11 @@ CVB200_API int cvb200_memset(void* dptr, int value, size_t bytes, cvb200_stream_
 CVB200_API int cvb200_stream_create(cvb200_stream_t* stream);
 CVB200_API int cvb200_stream_destroy(cvb200_stream_t stream);
 CVB200_API int cvb200_stream_sync(cvb200_stream_t stream);
+/* Caps the host worker pool used by the few per-frame host stages that remain (SHT line ordering); 0 = one per core (at most 128).
+ * A multi-process launch (one rank per GPU) sets it to cores / local ranks.  Reference: CompVBase::init(numThreads), base/compv_base.cxx. */
+CVB200_API int cvb200_set_host_threads(int n);
+/* Test hook (no device needed): out[i] += 1 for i in [0, n) through the host worker pool. */
+CVB200_API int cvb200_selftest_host_pool(size_t n, unsigned int* out);
 
 /* ================================================================================================
  * a2 -- separable convolution. Replaces CompVMathConvlt::convlt1<In,Kern,Out> / convlt1FixedPoint

@@ -55,3 +55,18 @@ def test_product_never_references_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("import oracle", "from oracle", "libcompv_oracle", "libcompv_ref"):
                     assert needle not in txt, "%s mentions %s" % (os.path.join(dirpath, f), needle)
+
+
+def test_host_pool_grows_between_calls_without_losing_items():
+    """The host worker pool (runtime.cu) grows when a call brings more items than any before: a worker created then must not replay the
+    previous, finished job (round-1 defect: a call could return with items unprocessed).  No GPU involved."""
+    import numpy as np
+    from compv_b200 import _ffi
+    lib = _ffi.lib()
+    lib.cvb200_set_host_threads(64)
+    for rep in range(200):
+        for n in (2, 256, 3, 97):
+            out = np.zeros(n, np.uint32)
+            assert lib.cvb200_selftest_host_pool(_ffi.sz(n), _ffi.vp(out)) == 0
+            assert (out == 1).all(), "rep %d n %d: %d items not processed exactly once" % (rep, n, int((out != 1).sum()))
+    lib.cvb200_set_host_threads(0)
