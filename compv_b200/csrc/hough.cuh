@@ -11,6 +11,11 @@ struct cvb200_hough {
 	bool x86Simd;
 	double lastGs;
 	// KHT scratch (hough_kht.cu)
+	cvb::DevBuf sortItems, sortLists, sortRanges, dLines, dCounts, tabs;
+	cvb::HostBuf hTabs;
+	size_t posCapEl = 0, strCapEl = 0, voteCapEl = 0;   // element capacities of the shared pools (grow-only)
+	double tabRho = 0, tabTheta = 0, tabR = 0; size_t tabNRho = 0;
+	size_t pendBatch = 0, pendCapacity = 0; cudaStream_t pendStream = nullptr; // what kht_enqueue left for kht_finish
 	cvb::DevBuf bits, poss, strings, strRev, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
 	cvb::HostBuf hFrames, hVotes, hCounts;
 	// SHT scratch (hough_sht.cu)
@@ -19,6 +24,8 @@ struct cvb200_hough {
 };
 
 namespace cvb {
+int kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, size_t capacity, cudaStream_t stream);
+int kht_finish(cvb200_hough* h, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, bool* again);
 int kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
 	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream);
 int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,

@@ -17,6 +17,7 @@
 // Host: the thresholded, smoothed cells (a few thousand per frame) are sorted with the same libstdc++ std::sort as the reference and swept.
 #include "hough.cuh"
 #include "kht_walk.cuh"
+#include "std_sort_emu.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -49,6 +50,8 @@ struct KhtFrame {           // per-frame offsets into the batch-wide pools + dev
 	unsigned int nPos, nStr, nClus, nVotes;
 	unsigned long long hmaxBits, gminBits;
 	double gs;
+	unsigned long long voteOff;       // this frame's cells in the vote / sort pools
+	unsigned int skip, pad;           // set when the position pools are too small: the linking kernel does nothing
 };
 struct KhtStack { unsigned int a, b, mi, nclus0; double ratio, ratioLeft; unsigned int state, pad; };
 
@@ -81,148 +84,8 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&edgeCount[frame], c);
 }
 
-// ---- linking ------------------------------------------------------------------------------------
-// The walk is a single dependent instruction chain on one lane: its cost is (instructions per step) x (issue latency, ~4 cycles).  Measured on frame G
-// (82k edge px, 5.9k walks per 1080p frame): three bitmap row loads per step 20.8 ms (~110 instr/step); shared-memory band caches 30-47 ms; a 3-row x 64-column
-// register window with bounds checks 16.0 ms (91 instr/step, ncu r1c); without bounds checks, running pointers 13.3 ms (~80 instr/step).  This version is written
-// for instruction count: the bitmap is zero padded on all four sides so the walker has no border case at all, the window lives in six 32-bit registers,
-// the position is one packed register (x | y << 16, the value that gets stored), the 9-bit neighbourhood is assembled in the order of Algorithm 6
-// (houghkht.cxx:666-703: TL, T, TR, L, [centre, already erased], R, BL, B, BR) so that one find-first-set yields k with dx = k % 3 - 1, dy = k / 3 - 1.
-// Every access to a frame's bitmap comes from this one warp, so its SM's L1 stays coherent with the stores.
 #define KHT_AHEAD 96
-struct KhtWalk {
-	unsigned int t0, t1, c0, c1, b0, b1; // bitmap rows y-1, y, y+1: padded columns [32*wb, 32*wb + 64)
-	unsigned int* p;                     // &paddedRow(y)[wb]
-	int rel;                             // padded column - 32*wb, kept in [1, 62]
-	unsigned int xy;                     // x | y << 16 (image coordinates)
-};
-
-__device__ __forceinline__ void kht_walk_load(KhtWalk& w, unsigned int* bits /* padded row 0 of the frame */, int WW)
-{
-	const int X = static_cast<int>(w.xy & 0xffffu) + 32, y = static_cast<int>(w.xy >> 16);
-	const int wi = X >> 5; // >= 1
-	const int wb = ((X & 31) < 16) ? wi - 1 : wi; // the pixel sits in columns [16, 47] of the window; wb + 1 <= WW - 1
-	w.rel = X - (wb << 5);
-	w.p = bits + y * WW + wb;
-	w.t0 = w.p[-WW]; w.t1 = w.p[1 - WW];
-	w.c0 = w.p[0]; w.c1 = w.p[1];
-	w.b0 = w.p[WW]; w.b1 = w.p[WW + 1];
-}
-
-__device__ __forceinline__ unsigned int kht_shr64(unsigned int lo, unsigned int hi, int sh) // low word of (hi:lo) >> sh, sh in [0, 63]
-{
-	return static_cast<unsigned int>(((static_cast<unsigned long long>(hi) << 32) | lo) >> sh);
-}
-
-// erase the current pixel in the registers and in memory
-__device__ __forceinline__ void kht_walk_erase(KhtWalk& w)
-{
-	const unsigned int mask = 1u << (w.rel & 31);
-	const int hi = w.rel >> 5;
-	if (hi) w.c1 &= ~mask; else w.c0 &= ~mask;
-	w.p[hi] = hi ? w.c1 : w.c0;
-}
-
-// move to the next pixel of the string; false when the current (already erased) pixel has no neighbour left
-__device__ __forceinline__ bool kht_walk_next(KhtWalk& w, unsigned int* bits, int WW)
-{
-	const int sh = w.rel - 1;
-	unsigned int m = kht_shr64(w.t0, w.t1, sh) & 7u;
-	m |= (kht_shr64(w.c0, w.c1, sh) & 7u) << 3;
-	m |= (kht_shr64(w.b0, w.b1, sh) & 7u) << 6;
-	if (!m) return false;
-	const int k = __ffs(m) - 1;           // 0..8 (never 4: the centre is erased)
-	const int dy1 = (k * 11) >> 5;        // k / 3
-	const int dx1 = k - 3 * dy1;          // k % 3
-	w.rel += dx1 - 1;
-	w.xy += static_cast<unsigned int>(dx1 + (dy1 << 16) - 65537);
-	if (static_cast<unsigned int>(w.rel - 1) > 61u) { kht_walk_load(w, bits, WW); return true; } // left the window sideways: re-centre
-	if (dy1 == 0) { w.p -= WW; w.b0 = w.c0; w.b1 = w.c1; w.c0 = w.t0; w.c1 = w.t1; w.t0 = w.p[-WW]; w.t1 = w.p[1 - WW]; }
-	else if (dy1 == 2) { w.p += WW; w.t0 = w.c0; w.t1 = w.c1; w.c0 = w.b0; w.c1 = w.b1; w.b0 = w.p[WW]; w.b1 = w.p[WW + 1]; }
-	return true;
-}
-
-__global__ void __launch_bounds__(32)
-kht_link_old_kernel(unsigned int* bitsAll /* read and written through several derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, KhtFrame* frames, KhtGeom g)
-{
-	const int frame = blockIdx.x, lane = threadIdx.x;
-	const int W = g.W, H = g.H, WW = g.WW;
-	unsigned int* bits = bitsAll + (static_cast<size_t>(frame) * (H + 2 * KHT_PADR) + KHT_PADR) * WW; // padded word 0 of image row 0
-	KhtFrame& fr = frames[frame];
-	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff); // ushort2 {x, y} written as x | y << 16
-	uint2* strings = stringsAll + fr.strOff;
-	unsigned int nPos = 0, nStr = 0; // meaningful on lane 0
-	const int lastWord = (W - 1) >> 5;
-
-	// The seed scan reads rows in order, so rows above the scan line are in this SM's L1; walks mostly head DOWN into rows nobody has read yet and
-	// would pay an L2 round trip per new row (the chain's dominant latency).  The idle lanes therefore keep KHT_AHEAD rows below the scan line prefetched.
-	const char* bytes0 = reinterpret_cast<const char*>(bits - WW);                       // padded row -1
-	const size_t bytesEnd = static_cast<size_t>(H + 3) * WW * 4;
-	for (size_t o = static_cast<size_t>(lane) * 128; o < bytesEnd && o < static_cast<size_t>(KHT_AHEAD + 2) * WW * 4; o += 32 * 128)
-		asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
-	for (int y = 1; y < H - 1; ++y) {
-		const unsigned int* row = bits + static_cast<size_t>(y) * WW + 1; // word 0 of the image row
-		{
-			const size_t o = static_cast<size_t>(y + 1 + KHT_AHEAD) * WW * 4 + static_cast<size_t>(lane) * 128; // row y + KHT_AHEAD, one 128-byte line per lane
-			if (o < bytesEnd && lane * 128 < WW * 4 + 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
-		}
-		for (int wb = 0; wb <= lastWord; wb += 32) {
-			while (true) {
-				const int wi = wb + lane;
-				unsigned int w = (wi <= lastWord) ? row[wi] : 0u; // plain load: served by this SM's L1, which the walker's stores keep current
-				// seeds are interior columns only: x in [1, W-2]
-				if (wi == 0) w &= ~1u;
-				if (wi == lastWord) w &= ~(1u << ((W - 1) & 31));
-				const unsigned int any = __ballot_sync(0xffffffffu, w != 0);
-				if (!any) break;
-				const int src = __ffs(any) - 1;
-				const unsigned int sw = __shfl_sync(0xffffffffu, w, src);
-				const int xr = (wb + src) * 32 + (__ffs(sw) - 1);
-				unsigned int begin = 0, rev = 0, end = 0;
-				if (lane == 0) {
-					// Algorithm 5 (houghkht.cxx:706-760)
-					begin = nPos;
-					unsigned int* out = poss + nPos;
-					KhtWalk wk;
-					wk.xy = static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16);
-					kht_walk_load(wk, bits, WW);
-					do {
-						*out++ = wk.xy;
-						kht_walk_erase(wk);
-					} while (kht_walk_next(wk, bits, WW));
-					rev = static_cast<unsigned int>(out - poss);
-					wk.xy = static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16);
-					kht_walk_load(wk, bits, WW);
-					if (kht_walk_next(wk, bits, WW)) {
-						do {
-							*out++ = wk.xy;
-							kht_walk_erase(wk);
-						} while (kht_walk_next(wk, bits, WW));
-					}
-					nPos = static_cast<unsigned int>(out - poss);
-					end = nPos;
-					if (end - begin < g.minSize) { nPos = begin; end = begin; }
-					else strings[nStr++] = make_uint2(begin, end);
-				}
-				__syncwarp();
-				begin = __shfl_sync(0xffffffffu, begin, 0);
-				rev = __shfl_sync(0xffffffffu, rev, 0);
-				end = __shfl_sync(0xffffffffu, end, 0);
-				if (end > begin) { // the first walk is stored reversed (std::reverse, houghkht.cxx:752-755)
-					const unsigned int n = rev - begin;
-					for (unsigned int i = lane; i < n / 2; i += 32) {
-						const unsigned int a = poss[begin + i], b = poss[begin + n - 1 - i];
-						poss[begin + i] = b; poss[begin + n - 1 - i] = a;
-					}
-				}
-				__syncwarp();
-			}
-		}
-	}
-	if (lane == 0) { fr.nPos = nPos; fr.nStr = nStr; }
-}
-
-// ---- linking (new): see kht_walk.cuh for the walker ----------------------------------------------
+// ---- linking: see kht_walk.cuh for the walker ----------------------------------------------
 // One warp per frame: the 32 lanes find the next seed in raster order (32 bitmap words per ballot), lane 0 runs Algorithm 5 for it.  The first walk of a
 // string is stored in walk order; the reversal the reference applies (std::reverse, houghkht.cxx:752-755) is left to kht_reverse_kernel, which is parallel
 // over strings, instead of a load-after-store round trip through L2 between two walks.
@@ -235,6 +98,7 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointe
 	const int W = g.W, H = g.H, WW = g.WW;
 	unsigned int* base = bitsAll + (static_cast<size_t>(frame) * (H + 2 * KHT_PADR) + KHT_PADR) * WW; // padded word 0 of image row 0
 	KhtFrame& fr = frames[frame];
+	if (fr.skip) return;
 	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff); // ushort2 {x, y} written as x | y << 16
 	uint2* strings = stringsAll + fr.strOff;
 	unsigned int* revs = revAll + fr.strOff;
@@ -622,7 +486,12 @@ __device__ __forceinline__ bool kht_scanned(const KhtGeom& g, unsigned int ri, u
 	return false;
 }
 
-// pass 1: per (frame, theta row) count of qualifying cells; pass 2 (after a host-side-free device scan) writes them in order
+// Peak detection without the host (the reference: peaks_Section3_4, houghkht.cxx:1195-1247 and :1282-1308):
+//   kht_peaks_count   per (frame, theta row): number of qualifying cells
+//   kht_row_offsets   per frame: exclusive scan of its rows + the frame's total
+//   kht_offsets2      exclusive scan over the frames of the batch -> where each frame's cells go in the shared pools (overflow -> flag, the host grows the pools and retries)
+//   kht_peaks_emit    per (frame, theta row): the cells in the reference's scan order (row-major, ascending rho)
+//   kht_peaks_sort    per frame: libstdc++'s std::sort permutation (std_sort_emu.cuh) evaluated by the warps of one CTA, then the sweep as a rank comparison, then the lines
 __global__ void kht_peaks_count_kernel(const int* __restrict__ accAll, unsigned int* __restrict__ rowCount, KhtGeom g)
 {
 	const int frame = blockIdx.y;
@@ -643,54 +512,258 @@ __global__ void kht_peaks_count_kernel(const int* __restrict__ accAll, unsigned 
 	if (threadIdx.x == 0) rowCount[frame * (g.nTheta + 2) + ti] = sSum;
 }
 
+// block-wide exclusive scan helper (blockDim.x == 256): returns the exclusive prefix of v, *total = the block's sum
+__device__ __forceinline__ unsigned int block_scan_256(unsigned int v, unsigned int* sWarp /* [9] shared */, unsigned int* total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned int inc = v;
+	for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+	__syncthreads(); // protects sWarp against the previous use
+	if (lane == 31) sWarp[warp] = inc;
+	__syncthreads();
+	if (threadIdx.x == 0) { unsigned int run = 0; for (int w = 0; w < 8; ++w) { const unsigned int t = sWarp[w]; sWarp[w] = run; run += t; } sWarp[8] = run; }
+	__syncthreads();
+	*total = sWarp[8];
+	return sWarp[warp] + inc - v;
+}
+
+// rowCount[frame][ti] (counts) -> exclusive offsets inside the frame; frames[frame].nVotes = the frame's total
+__global__ void __launch_bounds__(256) kht_row_offsets_kernel(unsigned int* __restrict__ rowCount, KhtFrame* frames, KhtGeom g)
+{
+	__shared__ unsigned int sWarp[9];
+	const int frame = blockIdx.x;
+	unsigned int* rc = rowCount + frame * (g.nTheta + 2);
+	unsigned int carry = 0;
+	for (unsigned int base = 1; base < g.nTheta; base += 256) {
+		const unsigned int ti = base + threadIdx.x;
+		const unsigned int c = (ti < g.nTheta) ? rc[ti] : 0u;
+		unsigned int total;
+		const unsigned int ex = block_scan_256(c, sWarp, &total);
+		if (ti < g.nTheta) rc[ti] = carry + ex;
+		carry += total;
+	}
+	if (threadIdx.x == 0) frames[frame].nVotes = carry;
+}
+
+struct KhtMeta { unsigned int overflow; unsigned int pad; unsigned long long needPos, needStr, needVotes; };
+
+// per-frame offsets into the position / string pools from the edge counts (one block; batch frames)
+__global__ void __launch_bounds__(256) kht_offsets1_kernel(const unsigned int* __restrict__ edgeCount, KhtFrame* frames, KhtMeta* meta, int batch, unsigned int minSize,
+	unsigned long long posCap, unsigned long long strCap)
+{
+	__shared__ unsigned int sWarp[9];
+	unsigned long long posRun = 0, strRun = 0;
+	for (int base = 0; base < batch; base += 256) {
+		const int f = base + threadIdx.x;
+		const unsigned int c = (f < batch) ? edgeCount[f] : 0u;
+		const unsigned int pc = (f < batch) ? c + 2u : 0u, sc = (f < batch) ? c / minSize + 1u : 0u;
+		unsigned int pt, st;
+		const unsigned int pe = block_scan_256(pc, sWarp, &pt);
+		const unsigned int se = block_scan_256(sc, sWarp, &st);
+		if (f < batch) {
+			KhtFrame fr;
+			memset(&fr, 0, sizeof(fr));
+			fr.posOff = static_cast<unsigned int>(posRun + pe); fr.posCap = c;
+			fr.strOff = static_cast<unsigned int>(strRun + se); fr.strCap = sc;
+			fr.gminBits = 0x7FEFFFFFFFFFFFFFull; fr.gs = 1.0;
+			frames[f] = fr;
+		}
+		posRun += pt; strRun += st;
+	}
+	__syncthreads();
+	const bool over = posRun + 1 > posCap || strRun + 1 > strCap || posRun >= (1ull << 31) || strRun >= (1ull << 31);
+	if (threadIdx.x == 0) { meta->needPos = posRun + 1; meta->needStr = strRun + 1; meta->needVotes = 0; meta->overflow = over ? 1u : 0u; }
+	if (over) for (int f = threadIdx.x; f < batch; f += 256) frames[f].skip = 1; // nothing downstream runs: every per-frame count stays 0
+}
+
+__global__ void __launch_bounds__(256) kht_offsets2_kernel(KhtFrame* frames, KhtMeta* meta, int batch, unsigned long long voteCap)
+{
+	__shared__ unsigned int sWarp[9];
+	unsigned long long run = 0;
+	for (int base = 0; base < batch; base += 256) {
+		const int f = base + threadIdx.x;
+		const unsigned int c = (f < batch) ? frames[f].nVotes : 0u;
+		unsigned int t;
+		const unsigned int e = block_scan_256(c, sWarp, &t);
+		if (f < batch) frames[f].voteOff = run + e;
+		run += t;
+	}
+	if (threadIdx.x == 0) { meta->needVotes = run + 1; if (run + 1 > voteCap) meta->overflow |= 2u; }
+}
+
 struct KhtVote { unsigned int rho_index, theta_index; int count; };
 
 __global__ void __launch_bounds__(256)
-kht_peaks_emit_kernel(const int* __restrict__ accAll, const unsigned int* __restrict__ rowCount, KhtVote* __restrict__ votesAll, unsigned int votesCap, KhtFrame* frames, KhtGeom g)
+kht_peaks_emit_kernel(const int* __restrict__ accAll, const unsigned int* __restrict__ rowOff, KhtVote* __restrict__ votesAll, const KhtFrame* frames, const KhtMeta* meta, KhtGeom g)
 {
-	// one block per frame: rows in order, cells of a row in ascending rho by chunks of 256 with a block scan
-	__shared__ unsigned int sScan[256];
-	__shared__ unsigned int sBase;
-	const int frame = blockIdx.x;
+	__shared__ unsigned int sWarp[9];
+	if (meta->overflow) return;
+	const int frame = blockIdx.y;
+	const unsigned int ti = blockIdx.x + 1;
+	if (ti >= g.nTheta) return;
+	const unsigned int* ro = rowOff + frame * (g.nTheta + 2);
+	const unsigned int next = (ti + 1 < g.nTheta) ? ro[ti + 1] : frames[frame].nVotes;
+	if (next == ro[ti]) return; // block-uniform: nothing in this row
 	const int* acc = accAll + static_cast<size_t>(frame) * (g.nTheta + 2) * g.cs;
-	KhtVote* votes = votesAll + static_cast<size_t>(frame) * votesCap;
-	if (threadIdx.x == 0) sBase = 0;
+	KhtVote* votes = votesAll + frames[frame].voteOff + ro[ti];
+	unsigned int carry = 0;
+	for (unsigned int base = 1; base < g.nRho; base += 256) {
+		const unsigned int ri = base + threadIdx.x;
+		unsigned int rep = 0; int v = 0;
+		const unsigned int ok = (kht_scanned(g, ri, rep) && kht_cell(acc, g, ti, ri, v)) ? 1u : 0u;
+		unsigned int total;
+		const unsigned int ex = block_scan_256(ok, sWarp, &total);
+		if (ok) { KhtVote o; o.rho_index = rep; o.theta_index = ti; o.count = v; votes[carry + ex] = o; }
+		carry += total;
+	}
+}
+
+// ---- std::sort's permutation + the sweep, one CTA per frame ----
+#define KSORT_THREADS 256
+#define KSORT_WARPS (KSORT_THREADS / 32)
+#define KSORT_SMEM_ITEMS 6144 // up to this many cells the whole sort runs in shared memory: 6144 * (8 + 4 + 4) bytes = 96 KB
+
+// one partition step of a[first, last) by one warp: the closed form of std_sort_emu.cuh (sse_partition_closed_form) with ballots for the two ordered compactions
+__device__ int ksort_warp_partition(sse_item* a, int first, int last, unsigned int* Ls, unsigned int* Rs)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned int lt = (1u << lane) - 1u;
+	if (lane == 0) sse_move_median_to_first(a, first, first + 1, first + (last - first) / 2, last - 1);
+	__syncwarp();
+	const unsigned int pk = sse_key(a[first]);
+	int nL = 0, nR = 0;
+	for (int base = first + 1; base < last; base += 32) {
+		const int i = base + lane;
+		const bool flag = i < last && !(sse_key(a[i]) > pk);
+		const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+		if (flag) Ls[first + nL + __popc(bal & lt)] = static_cast<unsigned int>(i);
+		nL += __popc(bal);
+	}
+	for (int base = last - 1; base > first; base -= 32) {
+		const int i = base - lane;
+		const bool flag = i > first && !(pk > sse_key(a[i]));
+		const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+		if (flag) Rs[first + nR + __popc(bal & lt)] = static_cast<unsigned int>(i);
+		nR += __popc(bal);
+	}
+	__syncwarp();
+	const int m = nL < nR ? nL : nR;
+	int K = 0;
+	for (int base = 0; base < m; base += 32) { // L ascends and R descends: the predicate is monotone, stop at the first chunk that contains a false
+		const int k = base + lane;
+		const bool ok = k < m && Ls[first + k] < Rs[first + k];
+		const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+		K += __popc(bal);
+		if (bal != 0xffffffffu) break;
+	}
+	for (int k = lane; k < K; k += 32) { const unsigned int i = Ls[first + k], j = Rs[first + k]; const sse_item t = a[i]; a[i] = a[j]; a[j] = t; }
+	const unsigned int cl = (K < nL) ? Ls[first + K] : 0xffffffffu;
+	const unsigned int cr = (K > 0) ? Rs[first + K - 1] : static_cast<unsigned int>(last);
+	__syncwarp();
+	return static_cast<int>(cl < cr ? cl : cr);
+}
+
+__global__ void __launch_bounds__(KSORT_THREADS)
+kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict__ itemsAll, unsigned int* __restrict__ listsAll, int* __restrict__ rangesAll, int* __restrict__ accAll,
+	const double* __restrict__ rhoTab, const double* __restrict__ thetaTab, cvb200_hough_line_t* __restrict__ lines, unsigned long long capacity, unsigned long long* __restrict__ counts,
+	const KhtFrame* frames, const KhtMeta* meta, KhtGeom g, unsigned int lim)
+{
+	extern __shared__ __align__(16) unsigned char ksortSmem[];
+	__shared__ unsigned int sWarp[9];
+	__shared__ int sCnt[2], sLeaves;
+	const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (meta->overflow) { if (tid == 0) counts[frame] = 0; return; }
+	const KhtFrame& fr = frames[frame];
+	const int nv = static_cast<int>(fr.nVotes);
+	if (nv == 0) { if (tid == 0) counts[frame] = 0; return; }
+	const KhtVote* votes = votesAll + fr.voteOff;
+	sse_item* a; unsigned int* Ls; unsigned int* Rs;
+	if (nv <= KSORT_SMEM_ITEMS) { a = reinterpret_cast<sse_item*>(ksortSmem); Ls = reinterpret_cast<unsigned int*>(a + KSORT_SMEM_ITEMS); Rs = Ls + KSORT_SMEM_ITEMS; }
+	else { a = itemsAll + fr.voteOff; Ls = listsAll + 2 * fr.voteOff; Rs = Ls + nv; }
+	for (int i = tid; i < nv; i += KSORT_THREADS) a[i] = (static_cast<sse_item>(static_cast<unsigned int>(votes[i].count)) << 32) | static_cast<unsigned int>(i);
 	__syncthreads();
-	for (unsigned int ti = 1; ti < g.nTheta; ++ti) {
-		if (rowCount[frame * (g.nTheta + 2) + ti] == 0) continue; // block-uniform
-		for (unsigned int base = 1; base < g.nRho; base += 256) {
-			const unsigned int ri = base + threadIdx.x;
-			unsigned int rep = 0; int v = 0;
-			const unsigned int ok = (kht_scanned(g, ri, rep) && kht_cell(acc, g, ti, ri, v)) ? 1u : 0u;
-			sScan[threadIdx.x] = ok;
-			__syncthreads();
-			for (int o = 1; o < 256; o <<= 1) {
-				const unsigned int u = (threadIdx.x >= o) ? sScan[threadIdx.x - o] : 0;
-				__syncthreads();
-				sScan[threadIdx.x] += u;
-				__syncthreads();
+
+	if (nv <= 96) { if (tid == 0) sse_sort_serial(a, nv); }
+	else {
+		// level-synchronous evaluation of the recursion tree: ranges of one level are disjoint and independent
+		int* leaves = rangesAll + 2 * fr.voteOff;             // (first, last) pairs of ranges with 2..16 elements: at most nv / 2 of them
+		int* lvl[2] = { leaves + nv, leaves + nv + nv / 2 };   // (first, last, depth) triples of ranges > 16 elements: at most nv / 17 per level, room for nv / 6
+		if (tid == 0) { lvl[0][0] = 0; lvl[0][1] = nv; lvl[0][2] = sse_lg(static_cast<unsigned int>(nv)) * 2; sCnt[0] = 1; sCnt[1] = 0; sLeaves = 0; }
+		__syncthreads();
+		for (int cur = 0;; cur ^= 1) {
+			const int cnt = sCnt[cur];
+			if (cnt == 0) break;
+			for (int r = warp; r < cnt; r += KSORT_WARPS) {
+				const int f = lvl[cur][3 * r], l = lvl[cur][3 * r + 1], d = lvl[cur][3 * r + 2];
+				if (d == 0) { if (lane == 0) sse_heap_sort(a + f, l - f); __syncwarp(); continue; } // the depth-limit fallback of introsort
+				const int cut = ksort_warp_partition(a, f, l, Ls, Rs);
+				if (lane < 2) {
+					const int cf = lane ? cut : f, cl = lane ? l : cut;
+					if (cl - cf > SSE_THRESHOLD) { const int k = atomicAdd(&sCnt[cur ^ 1], 1); lvl[cur ^ 1][3 * k] = cf; lvl[cur ^ 1][3 * k + 1] = cl; lvl[cur ^ 1][3 * k + 2] = d - 1; }
+					else if (cl - cf > 1) { const int k = atomicAdd(&sLeaves, 1); leaves[2 * k] = cf; leaves[2 * k + 1] = cl; }
+				}
 			}
-			const unsigned int pos = sBase + sScan[threadIdx.x] - ok;
-			if (ok && pos < votesCap) { KhtVote o; o.rho_index = rep; o.theta_index = ti; o.count = v; votes[pos] = o; }
 			__syncthreads();
-			if (threadIdx.x == 255) sBase += sScan[255];
+			if (tid == 0) sCnt[cur] = 0;
 			__syncthreads();
 		}
+		for (int k = tid; k < sLeaves; k += KSORT_THREADS) sse_insertion_sort(a, leaves[2 * k], leaves[2 * k + 1]);
 	}
-	if (threadIdx.x == 0) frames[frame].nVotes = sBase;
+	__syncthreads();
+
+	// ---- the sweep (houghkht.cxx:1207-1247).  The reference marks EVERY cell it visits, line or not, so "a neighbour was visited" == "a neighbour comes earlier in
+	// the sorted order": cell p is a line iff no vote of smaller sorted rank sits on one of its 8 neighbouring (theta, reported rho) positions.  The accumulator of this
+	// frame has been consumed by kht_peaks_emit and is reused as the rank map.
+	int* map = accAll + static_cast<size_t>(frame) * (g.nTheta + 2) * g.cs;
+	const int cs = static_cast<int>(g.cs);
+	for (int p = tid; p < nv; p += KSORT_THREADS) {
+		const KhtVote v = votes[static_cast<unsigned int>(a[p])];
+		int* c = map + static_cast<size_t>(v.theta_index) * cs + v.rho_index;
+		c[-cs - 1] = INT_MAX; c[-cs] = INT_MAX; c[-cs + 1] = INT_MAX; c[-1] = INT_MAX; c[0] = INT_MAX; c[1] = INT_MAX; c[cs - 1] = INT_MAX; c[cs] = INT_MAX; c[cs + 1] = INT_MAX;
+	}
+	__syncthreads();
+	for (int p = tid; p < nv; p += KSORT_THREADS) {
+		const KhtVote v = votes[static_cast<unsigned int>(a[p])];
+		atomicMin(map + static_cast<size_t>(v.theta_index) * cs + v.rho_index, p);
+	}
+	__syncthreads();
+	unsigned int nLines = 0;
+	for (int base = 0; base < nv; base += KSORT_THREADS) {
+		const int p = base + tid;
+		unsigned int isLine = 0;
+		KhtVote v; v.rho_index = 0; v.theta_index = 0; v.count = 0;
+		if (p < nv) {
+			v = votes[static_cast<unsigned int>(a[p])];
+			const int* c = map + static_cast<size_t>(v.theta_index) * cs + v.rho_index;
+			const bool seen = c[-cs - 1] < p || c[-cs] < p || c[-cs + 1] < p || c[-1] < p || c[1] < p || c[cs - 1] < p || c[cs] < p || c[cs + 1] < p;
+			isLine = seen ? 0u : 1u;
+		}
+		unsigned int total;
+		const unsigned int ex = block_scan_256(isLine, sWarp, &total);
+		const unsigned long long k = static_cast<unsigned long long>(nLines) + ex;
+		if (isLine && k < lim && k < capacity) {
+			cvb200_hough_line_t L;
+			L.rho = static_cast<float>(rhoTab[v.rho_index]);
+			L.theta = static_cast<float>((thetaTab[v.theta_index] * KHT_PI) / 180.0);
+			L.strength = static_cast<size_t>(v.count);
+			lines[static_cast<unsigned long long>(frame) * capacity + k] = L;
+		}
+		nLines += total;
+	}
+	if (tid == 0) counts[frame] = nLines < lim ? nLines : lim;
 }
 
 } // namespace cvb
 
 using namespace cvb;
 
-
-int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
-	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream)
+// Everything up to the lines runs on the device with no host interaction: pools are shared by the frames of the batch, their per-frame offsets come from
+// device-side scans, and a pool that turns out too small raises a flag (nothing is written out of bounds) that kht_finish answers by growing it and running again.
+int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, size_t capacity, cudaStream_t stream)
 {
-	const auto tCall0 = std::chrono::steady_clock::now();
 	CVB_REQUIRE(width <= 65535 && height <= 65535, CVB200_E_OUT_OF_BOUND); // positions are stored as 16-bit coordinates
 	CVB_REQUIRE(h->clusterMinSize >= 2, CVB200_E_INVALID_PARAMETER);       // 1 makes the reference's recursion endless
+	CVB_REQUIRE(batch < (1u << 20), CVB200_E_OUT_OF_BOUND);
 	KhtGeom g;
 	memset(&g, 0, sizeof(g));
 	g.W = static_cast<int>(width); g.H = static_cast<int>(height); g.WW = static_cast<int>(div_up(width, 32) + 2);
@@ -706,88 +779,81 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	const size_t nTheta = static_cast<size_t>(180.0 / g.dThetaDeg);
 	CVB_REQUIRE(nRho >= 2 && nTheta >= 2 && nRho < (1u << 24) && nTheta < (1u << 16), CVB200_E_INVALID_PARAMETER);
 	g.nRho = static_cast<unsigned int>(nRho); g.nTheta = static_cast<unsigned int>(nTheta); g.cs = g.nRho + 2;
-	std::vector<double> rho(nRho + 1, 0.0), theta(nTheta + 1, 0.0);
-	{ double v = -(r * 0.5); for (size_t i = 1; i < nRho; ++i, v += g.dRho) rho[i] = v; }
-	{ double v = 0.0; for (size_t i = 1; i < nTheta; ++i, v += g.dThetaDeg) theta[i] = v; }
-	g.rhoMaxNeg = rho[1];
+	g.rhoMaxNeg = -(r * 0.5);
 	g.halfW = static_cast<double>(width) * 0.5; g.halfH = static_cast<double>(height) * 0.5;
 	g.minDeviation = static_cast<double>(h->clusterMinDeviation); g.minHeight = static_cast<double>(h->kernelMinHeight);
 	g.minSize = static_cast<unsigned int>(h->clusterMinSize);
 	g.threshold = static_cast<int>(h->threshold);
 	g.x86Simd = h->x86Simd ? 1 : 0;
+	// the rho / theta tables (accumulated additions, houghkht.cxx:519-537) live on the device; re-made only when the geometry changes
+	if (h->tabRho != g.dRho || h->tabTheta != g.dThetaDeg || h->tabR != r || !h->tabs.p) {
+		CVB_CUDA(cudaStreamSynchronize(stream)); // the previous upload (if any) has left the pinned staging buffer
+		CVB_CHECK(h->hTabs.ensure((nRho + nTheta + 2) * sizeof(double)));
+		CVB_CHECK(h->tabs.ensure((nRho + nTheta + 2) * sizeof(double)));
+		double* rho = h->hTabs.as<double>(); double* theta = rho + nRho + 1;
+		rho[0] = 0.0; theta[0] = 0.0;
+		{ double v = -(r * 0.5); for (size_t i = 1; i <= nRho; ++i, v += g.dRho) rho[i] = (i < nRho) ? v : 0.0; }
+		{ double v = 0.0; for (size_t i = 1; i <= nTheta; ++i, v += g.dThetaDeg) theta[i] = (i < nTheta) ? v : 0.0; }
+		CVB_CUDA(cudaMemcpyAsync(h->tabs.p, rho, (nRho + nTheta + 2) * sizeof(double), cudaMemcpyHostToDevice, stream));
+		h->tabRho = g.dRho; h->tabTheta = g.dThetaDeg; h->tabR = r; h->tabNRho = nRho;
+	}
+	const double* dRhoTab = h->tabs.as<double>(); const double* dThetaTab = dRhoTab + nRho + 1;
 
-	static const int linkVariant = getenv("CVB200_KHT_LINK") ? atoi(getenv("CVB200_KHT_LINK")) : 2; // TEMPORARY A/B switch: 0 = round-1 walker, 1 = window walker, 2 = window walker on bit-reversed words
-	// ---- phase 1: bitmap + edge counts ----
+	// ---- pools (grow-only; first call: a guess, afterwards whatever the largest call needed) ----
+	const size_t px = width * height * batch;
+	if (h->posCapEl < batch * 4) h->posCapEl = std::max<size_t>(px / 16, batch * 4 + 1024);      // ~6 % edge pixels
+	if (h->strCapEl < batch * 2) h->strCapEl = std::max<size_t>(h->posCapEl / g.minSize + batch, batch * 2 + 1024);
+	if (h->voteCapEl < 1024) h->voteCapEl = std::max<size_t>(batch * 8192, 65536);
 	const size_t bitWords = static_cast<size_t>(g.H + 2 * KHT_PADR) * g.WW;
-	CVB_CHECK(h->bits.ensure(batch * bitWords * 4));
-	CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream)); // the zero border rows / words the walker relies on
-	CVB_CHECK(h->edgeCount.ensure(batch * 4));
-	CVB_CHECK(h->hCounts.ensure(batch * 4));
-	CVB_CUDA(cudaMemsetAsync(h->edgeCount.p, 0, batch * 4, stream));
-	{
-		dim3 grid(static_cast<unsigned>(div_up(g.WW, 64)), static_cast<unsigned>(g.H), static_cast<unsigned>(batch));
-		CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
-		KernelScope ks_("kht_bits", stream);
-		if (linkVariant == 2 || linkVariant == 3) kht_bits_kernel<true><<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, h->edgeCount.as<unsigned int>());
-		else kht_bits_kernel<false><<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, h->edgeCount.as<unsigned int>());
-	}
-	CVB_LAUNCHED();
-	unsigned int* hCounts = h->hCounts.as<unsigned int>();
-	CVB_CUDA(cudaMemcpyAsync(hCounts, h->edgeCount.p, batch * 4, cudaMemcpyDeviceToHost, stream));
-	CVB_CUDA(cudaStreamSynchronize(stream));
-
-	// ---- pools sized by the edge counts ----
-	CVB_CHECK(h->hFrames.ensure(batch * sizeof(KhtFrame)));
-	KhtFrame* hf = h->hFrames.as<KhtFrame>();
-	size_t posTotal = 0, strTotal = 0;
-	const unsigned long long dblMaxBits = static_cast<unsigned long long>(0x7FEFFFFFFFFFFFFFull);
-	for (size_t f = 0; f < batch; ++f) {
-		memset(&hf[f], 0, sizeof(KhtFrame));
-		hf[f].posOff = static_cast<unsigned int>(posTotal); hf[f].posCap = hCounts[f];
-		hf[f].strOff = static_cast<unsigned int>(strTotal); hf[f].strCap = hCounts[f] / g.minSize + 1;
-		hf[f].gminBits = dblMaxBits; hf[f].gs = 1.0;
-		posTotal += hCounts[f] + 2; strTotal += hf[f].strCap;
-		CVB_REQUIRE(posTotal < (1ull << 31) && strTotal < (1ull << 31), CVB200_E_OUT_OF_BOUND);
-	}
 	const size_t accCells = static_cast<size_t>(g.nTheta + 2) * g.cs;
-	// every accumulator cell may qualify (threshold 1 on a busy frame); only when that worst case gets large is the list capped (overflow is detected below)
-	size_t votesCap = accCells;
-	if (batch * accCells * sizeof(KhtVote) > (256u << 20)) { votesCap = accCells / 4; if (votesCap < 65536) votesCap = 65536; if (votesCap > accCells) votesCap = accCells; }
+	CVB_CHECK(h->bits.ensure(batch * bitWords * 4));
+	CVB_CHECK(h->edgeCount.ensure(batch * 4 + sizeof(KhtMeta)));
 	CVB_CHECK(h->frames.ensure(batch * sizeof(KhtFrame)));
-	CVB_CHECK(h->poss.ensure((posTotal + 1) * sizeof(ushort2)));
-	CVB_CHECK(h->strings.ensure((strTotal + 1) * sizeof(uint2)));
-	CVB_CHECK(h->nClusStr.ensure((strTotal + 1) * 4));
-	CVB_CHECK(h->clus.ensure((posTotal + 1) * sizeof(uint2)));
-	CVB_CHECK(h->clusOrd.ensure((posTotal + 1) * sizeof(uint2)));
-	CVB_CHECK(h->stack.ensure((posTotal + 1) * sizeof(KhtStack)));
-	CVB_CHECK(h->kern.ensure((posTotal + 1) * sizeof(KhtKernel)));
+	CVB_CHECK(h->poss.ensure(h->posCapEl * sizeof(ushort2)));
+	CVB_CHECK(h->strings.ensure(h->strCapEl * sizeof(uint2)));
+	CVB_CHECK(h->strRev.ensure(h->strCapEl * 4));
+	CVB_CHECK(h->nClusStr.ensure(h->strCapEl * 4));
+	CVB_CHECK(h->clus.ensure(h->posCapEl * sizeof(uint2)));
+	CVB_CHECK(h->clusOrd.ensure(h->posCapEl * sizeof(uint2)));
+	CVB_CHECK(h->stack.ensure(h->posCapEl * sizeof(KhtStack)));
+	CVB_CHECK(h->kern.ensure(h->posCapEl * sizeof(KhtKernel)));
 	CVB_CHECK(h->acc.ensure(batch * accCells * 4));
 	CVB_CHECK(h->rowCount.ensure(batch * (g.nTheta + 2) * 4));
-	CVB_CHECK(h->votes.ensure(batch * votesCap * sizeof(KhtVote)));
-	CVB_CHECK(h->hVotes.ensure(batch * votesCap * sizeof(KhtVote)));
-	CVB_CUDA(cudaMemcpyAsync(h->frames.p, hf, batch * sizeof(KhtFrame), cudaMemcpyHostToDevice, stream));
-	CVB_CUDA(cudaMemsetAsync(h->acc.p, 0, batch * accCells * 4, stream));
+	CVB_CHECK(h->votes.ensure(h->voteCapEl * sizeof(KhtVote)));
+	CVB_CHECK(h->sortItems.ensure(h->voteCapEl * sizeof(sse_item)));
+	CVB_CHECK(h->sortLists.ensure(h->voteCapEl * 2 * 4));
+	CVB_CHECK(h->sortRanges.ensure(h->voteCapEl * 2 * 4));
+	CVB_CHECK(h->dLines.ensure(std::max<size_t>(batch * capacity, 1) * sizeof(cvb200_hough_line_t)));
+	CVB_CHECK(h->dCounts.ensure(batch * 8));
+	CVB_CHECK(h->hFrames.ensure(batch * sizeof(KhtFrame) + sizeof(KhtMeta)));
+	CVB_CHECK(h->hCounts.ensure(batch * 8));
+	unsigned int* dEdgeCount = h->edgeCount.as<unsigned int>();
+	KhtMeta* dMeta = reinterpret_cast<KhtMeta*>(h->edgeCount.as<unsigned char>() + ((batch * 4 + 15) & ~static_cast<size_t>(15)));
+	CVB_CHECK(h->edgeCount.ensure(((batch * 4 + 15) & ~static_cast<size_t>(15)) + sizeof(KhtMeta)));
+	dEdgeCount = h->edgeCount.as<unsigned int>();
+	dMeta = reinterpret_cast<KhtMeta*>(h->edgeCount.as<unsigned char>() + ((batch * 4 + 15) & ~static_cast<size_t>(15)));
 	KhtFrame* dFrames = h->frames.as<KhtFrame>();
 	const unsigned int B = static_cast<unsigned int>(batch);
 
-	CVB_CHECK(h->strRev.ensure((strTotal + 1) * 4));
-	if (linkVariant == 0) {
-		KernelScope ks_("kht_link", stream);
-		kht_link_old_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), dFrames, g);
-		CVB_LAUNCHED();
+	CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream)); // the zero border rows / words the walker relies on
+	CVB_CUDA(cudaMemsetAsync(dEdgeCount, 0, ((batch * 4 + 15) & ~static_cast<size_t>(15)) + sizeof(KhtMeta), stream));
+	CVB_CUDA(cudaMemsetAsync(h->acc.p, 0, batch * accCells * 4, stream));
+	{
+		dim3 grid(static_cast<unsigned>(div_up(g.WW, 64)), static_cast<unsigned>(g.H), B);
+		CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
+		KernelScope ks_("kht_bits", stream);
+		kht_bits_kernel<true><<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, dEdgeCount);
 	}
-	else {
-		{ KernelScope ks_("kht_link", stream);
-		  unsigned int* bp = h->bits.as<unsigned int>(); ushort2* pp = h->poss.as<ushort2>(); uint2* sp = h->strings.as<uint2>(); unsigned int* rp = h->strRev.as<unsigned int>();
-		  if (linkVariant == 1) kht_link_kernel<false, false><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g);
-		  else if (linkVariant == 2) kht_link_kernel<true, false><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g);
-		  else if (linkVariant == 3) kht_link_kernel<true, true><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g);
-		  else kht_link_kernel<false, true><<<B, 32, 0, stream>>>(bp, pp, sp, rp, dFrames, g); }
-		CVB_LAUNCHED();
-		{ KernelScope ks_("kht_reverse", stream);
-		  kht_reverse_kernel<<<dim3(8, B), 128, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames); }
-		CVB_LAUNCHED();
-	}
+	CVB_LAUNCHED();
+	{ KernelScope ks_("kht_offsets", stream);
+	  kht_offsets1_kernel<<<1, 256, 0, stream>>>(dEdgeCount, dFrames, dMeta, static_cast<int>(batch), g.minSize, h->posCapEl, h->strCapEl); }
+	CVB_LAUNCHED();
+	{ KernelScope ks_("kht_link", stream);
+	  kht_link_kernel<true, false><<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g); }
+	CVB_LAUNCHED();
+	{ KernelScope ks_("kht_reverse", stream);
+	  kht_reverse_kernel<<<dim3(8, B), 128, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames); }
+	CVB_LAUNCHED();
 	{ KernelScope ks_("kht_subdivide", stream);
 	  kht_subdivide_kernel<<<dim3(32, B), 64, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->clus.as<uint2>(), h->nClusStr.as<unsigned int>(), h->stack.as<KhtStack>(), dFrames, g); }
 	CVB_LAUNCHED();
@@ -809,63 +875,73 @@ int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, si
 	{ KernelScope ks_("kht_peaks_count", stream);
 	  kht_peaks_count_kernel<<<dim3(g.nTheta, B), 128, 0, stream>>>(h->acc.as<int>(), h->rowCount.as<unsigned int>(), g); }
 	CVB_LAUNCHED();
-	{ KernelScope ks_("kht_peaks_emit", stream);
-	  kht_peaks_emit_kernel<<<B, 256, 0, stream>>>(h->acc.as<int>(), h->rowCount.as<unsigned int>(), h->votes.as<KhtVote>(), static_cast<unsigned int>(votesCap), dFrames, g); }
+	{ KernelScope ks_("kht_offsets", stream);
+	  kht_row_offsets_kernel<<<B, 256, 0, stream>>>(h->rowCount.as<unsigned int>(), dFrames, g); }
 	CVB_LAUNCHED();
-	CVB_CUDA(cudaMemcpyAsync(hf, dFrames, batch * sizeof(KhtFrame), cudaMemcpyDeviceToHost, stream));
-	CVB_CUDA(cudaStreamSynchronize(stream));
-	for (size_t f = 0; f < batch; ++f) CVB_REQUIRE(hf[f].nVotes <= votesCap, CVB200_E_OUT_OF_BOUND);
-	KhtVote* hv = h->hVotes.as<KhtVote>();
+	{ KernelScope ks_("kht_offsets", stream);
+	  kht_offsets2_kernel<<<1, 256, 0, stream>>>(dFrames, dMeta, static_cast<int>(batch), h->voteCapEl); }
+	CVB_LAUNCHED();
+	{ KernelScope ks_("kht_peaks_emit", stream);
+	  kht_peaks_emit_kernel<<<dim3(g.nTheta, B), 256, 0, stream>>>(h->acc.as<int>(), h->rowCount.as<unsigned int>(), h->votes.as<KhtVote>(), dFrames, dMeta, g); }
+	CVB_LAUNCHED();
 	{
-		size_t maxVotes = 0; // one strided copy for the whole batch: the leading maxVotes cells of every frame's list
-		for (size_t f = 0; f < batch; ++f) maxVotes = std::max<size_t>(maxVotes, hf[f].nVotes);
-		if (maxVotes) CVB_CUDA(cudaMemcpy2DAsync(hv, votesCap * sizeof(KhtVote), h->votes.p, votesCap * sizeof(KhtVote), maxVotes * sizeof(KhtVote), batch, cudaMemcpyDeviceToHost, stream));
+		static std::once_flag once;
+		static cudaError_t attrErr = cudaSuccess;
+		const int smem = KSORT_SMEM_ITEMS * (8 + 4 + 4);
+		std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kht_peaks_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+		CVB_CUDA(attrErr);
+		const unsigned int lim = (h->maxLines <= 0) ? static_cast<unsigned int>(INT_MAX) : static_cast<unsigned int>(h->maxLines);
+		KernelScope ks_("kht_peaks_sort", stream);
+		kht_peaks_sort_kernel<<<B, KSORT_THREADS, smem, stream>>>(h->votes.as<KhtVote>(), h->sortItems.as<sse_item>(), h->sortLists.as<unsigned int>(), h->sortRanges.as<int>(), h->acc.as<int>(),
+			dRhoTab, dThetaTab, h->dLines.as<cvb200_hough_line_t>(), static_cast<unsigned long long>(capacity), h->dCounts.as<unsigned long long>(), dFrames, dMeta, g, lim);
 	}
-	CVB_CUDA(cudaStreamSynchronize(stream));
-	const auto tHost0 = std::chrono::steady_clock::now();
-
-	// ---- host: sort + sweep (houghkht.cxx:1195-1247). std::sort of the same libstdc++ on the same input order = the reference's tie order ----
-	// Frames are independent: a few host threads share them (the sort of a few thousand cells per frame is the only per-frame host work).
-	const size_t lim = (h->maxLines <= 0) ? static_cast<size_t>(INT_MAX) : static_cast<size_t>(h->maxLines);
-	host_parallel_for(batch, [&](size_t f) {
-		static thread_local std::vector<uint8_t> visited; // all zero between frames (the sweep clears what it marked)
-		if (visited.size() < accCells) visited.assign(accCells, 0);
-
-		KhtVote* v = hv + f * votesCap;
-		const size_t nv = hf[f].nVotes;
-		std::sort(v, v + nv, [](const KhtVote& a, const KhtVote& b) { return a.count > b.count; });
-		size_t n = 0;
-		for (size_t i = 0; i < nv; ++i) {
-			uint8_t* pv = &visited[static_cast<size_t>(v[i].theta_index) * g.cs + v[i].rho_index];
-			const uint8_t* t = pv - g.cs; const uint8_t* b = pv + g.cs;
-			const bool seen = t[-1] || t[0] || t[1] || pv[-1] || pv[1] || b[-1] || b[0] || b[1];
-			if (!seen) {
-				if (n < lim) {
-					if (n < capacity) {
-						cvb200_hough_line_t& L = lines[f * capacity + n];
-						L.rho = static_cast<float>(rho[v[i].rho_index]);
-						L.theta = static_cast<float>((theta[v[i].theta_index] * M_PI) / 180.0);
-						L.strength = static_cast<size_t>(v[i].count);
-					}
-					++n;
-				}
-			}
-			*pv = 0xff;
-		}
-		for (size_t i = 0; i < nv; ++i) visited[static_cast<size_t>(v[i].theta_index) * g.cs + v[i].rho_index] = 0;
-		counts[f] = n;
-	});
-	{
-		const size_t f = batch - 1;
-		h->lastGs = (hf[f].nStr && hf[f].nClus) ? hf[f].gs : 1.0;
-	}
-	if (getenv("CVB200_TRACE")) {
-		const auto t1 = std::chrono::steady_clock::now();
-		size_t nv = 0; for (size_t f = 0; f < batch; ++f) nv += hf[f].nVotes;
-		fprintf(stderr, "[cvb200] kht batch %zu: device+copies %.3f ms, host peaks %.3f ms (%zu cells)\n", batch,
-			std::chrono::duration<double, std::milli>(tHost0 - tCall0).count(), std::chrono::duration<double, std::milli>(t1 - tHost0).count(), nv);
-	}
+	CVB_LAUNCHED();
+	// results that the host always needs: the per-frame line counts + the overflow flag + the last frame's record (Gs)
+	unsigned char* hMeta = h->hFrames.as<unsigned char>();
+	CVB_CUDA(cudaMemcpyAsync(hMeta, dMeta, sizeof(KhtMeta), cudaMemcpyDeviceToHost, stream));
+	CVB_CUDA(cudaMemcpyAsync(hMeta + sizeof(KhtMeta), dFrames + (batch - 1), sizeof(KhtFrame), cudaMemcpyDeviceToHost, stream));
+	CVB_CUDA(cudaMemcpyAsync(h->hCounts.p, h->dCounts.p, batch * 8, cudaMemcpyDeviceToHost, stream));
+	h->pendBatch = batch; h->pendCapacity = capacity; h->pendStream = stream;
 	return CVB200_S_OK;
+}
+
+// Waits for kht_enqueue's work, hands out the lines.  Returns CVB200_E_PENDING-like internal code 1 when a pool was too small and has been grown: the caller enqueues again.
+int cvb::kht_finish(cvb200_hough* h, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, bool* again)
+{
+	*again = false;
+	cudaStream_t stream = h->pendStream;
+	const size_t batch = h->pendBatch;
+	CVB_CUDA(cudaStreamSynchronize(stream));
+	const KhtMeta* m = h->hFrames.as<KhtMeta>();
+	if (m->overflow) {
+		if (m->overflow & 1u) { h->posCapEl = std::max<size_t>(h->posCapEl, static_cast<size_t>(m->needPos + m->needPos / 4 + 1024)); h->strCapEl = std::max<size_t>(h->strCapEl, static_cast<size_t>(m->needStr + m->needStr / 4 + 1024)); }
+		if (m->overflow & 2u) h->voteCapEl = std::max<size_t>(h->voteCapEl, static_cast<size_t>(m->needVotes + m->needVotes / 4 + 1024));
+		CVB_REQUIRE(h->posCapEl < (1ull << 31) && h->strCapEl < (1ull << 31), CVB200_E_OUT_OF_BOUND);
+		*again = true;
+		return CVB200_S_OK;
+	}
+	const unsigned long long* hc = h->hCounts.as<unsigned long long>();
+	size_t maxLines = 0;
+	for (size_t f = 0; f < batch; ++f) { counts[f] = static_cast<size_t>(hc[f]); maxLines = std::max<size_t>(maxLines, std::min<size_t>(counts[f], capacity)); }
+	if (maxLines) { // one strided copy: the leading maxLines lines of every frame
+		CVB_CUDA(cudaMemcpy2DAsync(lines, capacity * sizeof(cvb200_hough_line_t), h->dLines.p, capacity * sizeof(cvb200_hough_line_t), maxLines * sizeof(cvb200_hough_line_t), batch, cudaMemcpyDeviceToHost, stream));
+		CVB_CUDA(cudaStreamSynchronize(stream));
+	}
+	const KhtFrame* last = reinterpret_cast<const KhtFrame*>(h->hFrames.as<unsigned char>() + sizeof(KhtMeta));
+	h->lastGs = (last->nStr && last->nClus) ? last->gs : 1.0;
+	return CVB200_S_OK;
+}
+
+int cvb::kht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch,
+	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream)
+{
+	for (int attempt = 0; attempt < 4; ++attempt) {
+		CVB_CHECK(kht_enqueue(h, edges, width, height, stride, batch, framePitch, capacity, stream));
+		bool again = false;
+		CVB_CHECK(kht_finish(h, lines, capacity, counts, &again));
+		if (!again) return CVB200_S_OK;
+	}
+	return CVB200_E_OUT_OF_BOUND;
 }
 
 extern "C" {
@@ -891,10 +967,10 @@ int cvb200_hough_free(cvb200_hough_t** hough)
 {
 	if (hough && *hough) {
 		cvb200_hough* h = *hough;
-		DevBuf* bufs[] = { &h->bits, &h->poss, &h->strings, &h->strRev, &h->clus, &h->clusOrd, &h->nClusStr, &h->stack, &h->kern, &h->acc, &h->rowCount, &h->votes, &h->frames, &h->edgeCount, &h->hostIn,
+		DevBuf* bufs[] = { &h->bits, &h->poss, &h->strings, &h->strRev, &h->sortItems, &h->sortLists, &h->sortRanges, &h->dLines, &h->dCounts, &h->tabs, &h->clus, &h->clusOrd, &h->nClusStr, &h->stack, &h->kern, &h->acc, &h->rowCount, &h->votes, &h->frames, &h->edgeCount, &h->hostIn,
 			&h->shtTables, &h->shtList, &h->shtCursor, &h->shtMask, &h->shtPool, &h->shtDesc };
 		for (DevBuf* b : bufs) b->release();
-		h->hFrames.release(); h->hVotes.release(); h->hCounts.release();
+		h->hFrames.release(); h->hVotes.release(); h->hCounts.release(); h->hTabs.release();
 		delete h;
 		*hough = nullptr;
 	}
