@@ -396,6 +396,15 @@ def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
     return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]
 
 
+def canny_kht_process_batch_dev(canny, hough, d_images, width, height, stride, batch, capacity=4096, frame_pitch=0, stream=0):
+    """Device frames -> list of per-frame line arrays (host); cvb200_canny_kht_process_batch_dev."""
+    lines = np.zeros((batch, capacity), LINE_DTYPE)
+    counts = np.zeros(batch, np.uint64)
+    check(lib().cvb200_canny_kht_process_batch_dev(canny._h, hough._h, vp(d_images), sz(width), sz(height), sz(stride), sz(batch), sz(frame_pitch), vp(lines), sz(capacity), vp(counts),
+                                                   C.c_void_p(stream)), "cvb200_canny_kht_process_batch_dev")
+    return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(batch)]
+
+
 # ---- a10: thresholding ------------------------------------------------------------------------------
 def histogram(img, width=None):
     """CompVMathHistogram::build (8-bit): 256 uint32 bins."""

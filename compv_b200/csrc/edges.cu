@@ -11,7 +11,7 @@
 //                 its result is exactly the set of {g>tLow} pixels 8-connected to a {g>tHigh} seed. Tiles are relaxed to a fixed point in shared
 //                 memory; a tile whose border pixels changed marks its neighbours dirty; rounds repeat until no tile is dirty.
 //   finalize    : WEAK -> 0, STRONG -> 0xff (in place).
-#include "common.cuh"
+#include "edge.cuh"
 
 #include <cooperative_groups.h>
 #include <cstring>
@@ -20,12 +20,7 @@ namespace cg = cooperative_groups;
 
 namespace cvb {
 
-// ---- kernel tables: base/include/compv/base/compv_features.h:124-133 ----
-struct EdgeTaps {
-	int16_t vt[5];
-	int16_t hz[5];
-	int ks;
-};
+// ---- kernel tables: base/include/compv/base/compv_features.h:124-133 (EdgeTaps / BlurTaps: edge.cuh) ----
 
 static int edge_taps(int id, size_t kernSize, EdgeTaps* t)
 {
@@ -57,10 +52,6 @@ static int edge_taps(int id, size_t kernSize, EdgeTaps* t)
 	}
 }
 
-struct BlurTaps {
-	float k[7];
-	int ks; // 0 = no blur; 3, 5 or 7
-};
 
 constexpr uint8_t CLS_WEAK = 0x80;
 constexpr uint8_t CLS_STRONG = 0xff;
@@ -275,23 +266,19 @@ struct HystParams {
 	int W, H;
 	size_t stride, framePitch;
 	int tilesX, tilesY, nTiles;     // nTiles = tilesX*tilesY*batch
-	unsigned char* dirtyIn;         // round > 0: process only tiles flagged here (and clear the flag)
-	unsigned char* dirtyOut;
-	unsigned int* changed;          // number of tiles whose border changed in this round
-	int firstRound;
+	int round;                      // 0: every tile (tile = blockIdx.x); r > 0: the tiles queued by round r-1
+	const int* listIn;              // round > 0: tile ids to visit
+	const unsigned int* countIn;
+	int* listOut;                   // tiles whose neighbourhood changed in this round: visited by round + 1
+	unsigned int* countOut;
+	int* epoch;                     // per tile: the last round it was queued for (a tile is queued at most once per round)
 };
 
-__global__ void __launch_bounds__(HT_THREADS)
-canny_hysteresis_kernel(const HystParams p)
+// One tile: load with a 1-px halo, relax to the fixed point inside the tile, write the promotions back, queue the neighbours that can see a change.
+__device__ __forceinline__ void hysteresis_tile(const HystParams& p, int tile, uint8_t* s, int* sBorder)
 {
-	__shared__ uint8_t s[HP * HP];
-	__shared__ int sBorder; // bit0 top, bit1 bottom, bit2 left, bit3 right
-	const int tile = blockIdx.x;
-	if (!p.firstRound) {
-		if (!p.dirtyIn[tile]) return;
-	}
 	const int tid = threadIdx.x;
-	if (tid == 0) { sBorder = 0; if (!p.firstRound) p.dirtyIn[tile] = 0; }
+	if (tid == 0) *sBorder = 0;
 	const int frame = tile / (p.tilesX * p.tilesY);
 	const int t2 = tile - frame * (p.tilesX * p.tilesY);
 	const int ty = t2 / p.tilesX, tx = t2 - ty * p.tilesX;
@@ -356,25 +343,34 @@ canny_hysteresis_kernel(const HystParams p)
 		}
 		if (ry == 0) b |= 1;
 		if (ry == HT - 1) b |= 2;
-		if (b) atomicOr(&sBorder, b);
+		if (b) atomicOr(sBorder, b);
 	}
 	__syncthreads();
-	if (tid == 0 && sBorder) {
-		const int b = sBorder;
-		const int base = frame * (p.tilesX * p.tilesY);
-		bool any = false;
-		for (int dy = -1; dy <= 1; ++dy) {
-			for (int dx = -1; dx <= 1; ++dx) {
-				if (!dx && !dy) continue;
-				if ((dy < 0 && !(b & 1)) || (dy > 0 && !(b & 2)) || (dx < 0 && !(b & 4)) || (dx > 0 && !(b & 8))) continue;
-				const int nx = tx + dx, ny = ty + dy;
-				if (nx < 0 || nx >= p.tilesX || ny < 0 || ny >= p.tilesY) continue;
-				p.dirtyOut[base + ny * p.tilesX + nx] = 1;
-				any = true;
-			}
+	if (tid < 9 && tid != 4 && *sBorder) {
+		// bit0 top, bit1 bottom, bit2 left, bit3 right: a neighbour tile is queued for the next round when a promoted pixel lies on the border it shares with this tile
+		const int b = *sBorder;
+		const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+		const bool sees = !((dy < 0 && !(b & 1)) || (dy > 0 && !(b & 2)) || (dx < 0 && !(b & 4)) || (dx > 0 && !(b & 8)));
+		const int nx = tx + dx, ny = ty + dy;
+		if (sees && nx >= 0 && nx < p.tilesX && ny >= 0 && ny < p.tilesY) {
+			const int nb = frame * (p.tilesX * p.tilesY) + ny * p.tilesX + nx;
+			if (atomicMax(&p.epoch[nb], p.round + 1) < p.round + 1) p.listOut[atomicAdd(p.countOut, 1u)] = nb;
 		}
-		if (any) atomicAdd(p.changed, 1u);
 	}
+	__syncthreads(); // s / sBorder are reused by the next tile of this CTA
+}
+
+// Round 0 visits every tile (grid = nTiles).  Later rounds run on a fixed small grid over the list the previous round queued: a round with nothing queued costs one
+// empty launch, so a fixed number of rounds can be issued without asking the host whether the previous one changed anything.
+template <bool FIRST>
+__global__ void __launch_bounds__(HT_THREADS)
+canny_hysteresis_kernel(const HystParams p)
+{
+	__shared__ uint8_t s[HP * HP];
+	__shared__ int sBorder;
+	if (FIRST) { hysteresis_tile(p, blockIdx.x, s, &sBorder); return; }
+	const unsigned int n = *p.countIn;
+	for (unsigned int i = blockIdx.x; i < n; i += gridDim.x) hysteresis_tile(p, p.listIn[i], s, &sBorder);
 }
 
 // WEAK -> 0 (in place). 16 pixels per thread; stores only where something changes.
@@ -482,20 +478,6 @@ static int launch_front(const FrontParams& p, int mode, size_t batch, cudaStream
 using namespace cvb;
 
 // The detector object: caches its scratch like the reference objects do (canny_dete.cxx:133-147)
-struct cvb200_edge_dete {
-	int id;
-	float tLow, tHigh;
-	int thresholdType;
-	EdgeTaps taps;
-	BlurTaps blur;
-	DevBuf dirty;      // 2 x nTiles bytes
-	DevBuf counters;   // per-round changed counters / per-frame gmax / sums / thresholds
-	HostBuf hostFlag;
-	DevBuf hostIn, hostOut; // staging for the host-buffer entry point
-	bool gmaxLanes;
-	bool genericKernel;     // CVB200_EDGE_SET_BOOL_GENERIC_KERNEL: force the generic front kernel (tests)
-	std::mutex mutex;
-};
 
 extern "C" {
 
@@ -589,16 +571,16 @@ int cvb200_edge_dete_set_preblur(cvb200_edge_dete_t* d, size_t size, float sigma
 	return CVB200_S_OK;
 }
 
-int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges,
-	size_t batch, size_t framePitch, cvb200_stream_t stream_)
+} // extern "C"
+
+// All the kernels of one call, issued on `stream` without host interaction (the caller holds d->mutex).  edge_finish completes the call.
+int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges, size_t batch, size_t framePitch, cudaStream_t stream)
 {
 	CVB_REQUIRE_INIT();
 	CVB_REQUIRE(d && image && edges && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
 	CVB_REQUIRE(width <= 0x3fffffff && height <= 0x3fffffff, CVB200_E_OUT_OF_BOUND);
-	if (!batch) return CVB200_S_OK;
 	if (!framePitch) framePitch = stride * height;
-	cudaStream_t stream = as_stream(stream_);
-	std::lock_guard<std::mutex> lock(d->mutex);
+	d->pendStream = stream; d->pendCheck = false;
 
 	FrontParams p;
 	memset(&p, 0, sizeof(p));
@@ -639,12 +621,10 @@ int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, si
 	const int tilesX = static_cast<int>(div_up(width, HT)), tilesY = static_cast<int>(div_up(height, HT));
 	const size_t nTiles = static_cast<size_t>(tilesX) * tilesY * batch;
 	CVB_REQUIRE(nTiles <= 0x7fffffff, CVB200_E_OUT_OF_BOUND);
-	CVB_CHECK(d->dirty.ensure(2 * nTiles));
-	const size_t countersBytes = 64 * sizeof(unsigned int) + batch * (sizeof(unsigned int) + sizeof(ushort2));
+	const size_t countersBytes = batch * (sizeof(unsigned int) + sizeof(ushort2));
 	CVB_CHECK(d->counters.ensure(countersBytes));
 	CVB_CHECK(d->hostFlag.ensure(64 * sizeof(unsigned int)));
-	unsigned int* changed = d->counters.as<unsigned int>();            // [64] per-round counters
-	unsigned int* sums = changed + 64;                                   // [batch]
+	unsigned int* sums = d->counters.as<unsigned int>();                 // [batch]
 	ushort2* thr = reinterpret_cast<ushort2*>(sums + batch);             // [batch]
 
 	if (d->thresholdType == CVB200_CANNY_THRESHOLD_TYPE_PERCENT_OF_MEAN) {
@@ -691,33 +671,31 @@ int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, si
 		CVB_CHECK(launch_front(p, 0, batch, stream));
 	}
 
-	// hysteresis rounds. Round 0 visits every tile; later rounds only tiles flagged dirty. Rounds are issued in groups of 4 without host
-	// interaction (a round with nothing dirty costs one empty launch); the host reads the last counter of a group to decide whether to go on.
+	// hysteresis: round 0 over every tile, then d->hystRounds list-driven rounds, all issued without host interaction.  Whether the last round still queued
+	// something (not converged: only for edges that snake through more tiles than there were rounds) is read back with the results; edge_finish then
+	// raises the number of rounds and the call is run again.
 	HystParams h;
 	h.cls = edges; h.W = p.W; h.H = p.H; h.stride = stride; h.framePitch = framePitch;
 	h.tilesX = tilesX; h.tilesY = tilesY; h.nTiles = static_cast<int>(nTiles);
-	unsigned char* dirtyA = d->dirty.as<unsigned char>();
-	unsigned char* dirtyB = dirtyA + nTiles;
-	CVB_CUDA(cudaMemsetAsync(dirtyA, 0, 2 * nTiles, stream));
-	unsigned int* hostFlag = d->hostFlag.as<unsigned int>();
-	int round = 0;
-	while (true) {
-		CVB_CUDA(cudaMemsetAsync(changed, 0, 4 * sizeof(unsigned int), stream));
-		for (int k = 0; k < 4; ++k, ++round) {
-			h.firstRound = (round == 0);
-			h.dirtyIn = (round & 1) ? dirtyB : dirtyA;
-			h.dirtyOut = (round & 1) ? dirtyA : dirtyB;
-			h.changed = changed + k;
-			{
-				KernelScope ks_("canny_hysteresis", stream);
-				canny_hysteresis_kernel<<<static_cast<unsigned>(nTiles), HT_THREADS, 0, stream>>>(h);
-			}
-			CVB_LAUNCHED();
-		}
-		CVB_CUDA(cudaMemcpyAsync(hostFlag, changed + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-		CVB_CUDA(cudaStreamSynchronize(stream));
-		if (hostFlag[0] == 0) break;
+	const int rounds = d->hystRounds;
+	CVB_CHECK(d->dirty.ensure(nTiles * 3 * sizeof(int) + (static_cast<size_t>(rounds) + 2) * sizeof(unsigned int)));
+	int* epoch = d->dirty.as<int>();
+	int* lists[2] = { epoch + nTiles, epoch + 2 * nTiles };
+	unsigned int* roundCount = reinterpret_cast<unsigned int*>(epoch + 3 * nTiles); // [rounds + 2]: roundCount[r] = tiles queued for round r
+	CVB_CUDA(cudaMemsetAsync(epoch, 0, nTiles * sizeof(int), stream));
+	CVB_CUDA(cudaMemsetAsync(roundCount, 0, (static_cast<size_t>(rounds) + 2) * sizeof(unsigned int), stream));
+	h.epoch = epoch;
+	for (int round = 0; round <= rounds; ++round) {
+		h.round = round;
+		h.listIn = lists[round & 1]; h.countIn = roundCount + round;
+		h.listOut = lists[(round + 1) & 1]; h.countOut = roundCount + round + 1;
+		KernelScope ks_("canny_hysteresis", stream);
+		if (round == 0) canny_hysteresis_kernel<true><<<static_cast<unsigned>(nTiles), HT_THREADS, 0, stream>>>(h);
+		else canny_hysteresis_kernel<false><<<static_cast<unsigned>(std::min<size_t>(nTiles, static_cast<size_t>(num_sms()) * 4)), HT_THREADS, 0, stream>>>(h);
+		CVB_LAUNCHED();
 	}
+	CVB_CUDA(cudaMemcpyAsync(d->hostFlag.p, roundCount + rounds + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+	d->pendCheck = true;
 
 	dim3 fg(static_cast<unsigned>(div_up(div_up(width, 16), 128)), static_cast<unsigned>(height), static_cast<unsigned>(batch));
 	CVB_REQUIRE(fg.y <= 65535, CVB200_E_OUT_OF_BOUND);
@@ -727,6 +705,40 @@ int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, si
 	}
 	CVB_LAUNCHED();
 	return CVB200_S_OK;
+}
+
+// Waits for edge_enqueue's work.  *again = the hysteresis had not converged within the rounds issued: their number has been raised, enqueue again.
+int cvb::edge_finish(cvb200_edge_dete* d, bool* again)
+{
+	*again = false;
+	CVB_CUDA(cudaStreamSynchronize(d->pendStream));
+	if (d->pendCheck) {
+		d->pendCheck = false;
+		if (d->hostFlag.as<unsigned int>()[0] != 0) {
+			CVB_REQUIRE(d->hystRounds < (1 << 20), CVB200_E_INVALID_STATE);
+			d->hystRounds *= 4;
+			*again = true;
+		}
+	}
+	return CVB200_S_OK;
+}
+
+extern "C" {
+
+int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges,
+	size_t batch, size_t framePitch, cvb200_stream_t stream_)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(d && image && edges && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
+	if (!batch) return CVB200_S_OK;
+	std::lock_guard<std::mutex> lock(d->mutex);
+	for (int attempt = 0; attempt < 12; ++attempt) {
+		CVB_CHECK(edge_enqueue(d, image, width, height, stride, edges, batch, framePitch, as_stream(stream_)));
+		bool again = false;
+		CVB_CHECK(edge_finish(d, &again));
+		if (!again) return CVB200_S_OK;
+	}
+	return CVB200_E_INVALID_STATE;
 }
 
 int cvb200_edge_dete_process(cvb200_edge_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges)

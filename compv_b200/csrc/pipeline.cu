@@ -1,64 +1,178 @@
-// Host-buffer pipeline for the headline workload (BASELINE.json: Canny + HoughKHT): frames in host memory -> lines in host memory.
-// The reference runs CompVEdgeDete::process then CompVHough::process on the CPU and the edge map travels through host memory between them
-// (samples/hough_lines/main.cxx:59,106).  Here the edge map never leaves the device: chunks of frames are copied in on a copy stream while the
-// previous chunk is in the Canny / KHT kernels, and only the detected lines come back.
-#include "common.cuh"
+// The headline workload (BASELINE.json: Canny + HoughKHT) as one pipelined call: frames (host or device memory) -> lines in host memory.
+// The reference runs CompVEdgeDete::process then CompVHough::process per frame on the CPU and the edge map travels through host memory between them
+// (samples/hough_lines/main.cxx:59,106).  Here the frames of a batch are cut into sub-batches that flow through a ring of SLOTS: every slot owns a stream,
+// a private copy of the two detector objects (their scratch is per object, as in the reference) and its edge maps.  Nothing inside a slot talks to the host
+// (device-side pool offsets, hysteresis rounds and peak ordering), so the host only enqueues; the sub-batches of neighbouring slots overlap on the GPU:
+// the KHT linking kernel of one sub-batch (one warp per frame: a latency chain that leaves the SMs almost empty) runs next to the Canny and voting kernels
+// of the others and, for host frames, next to the H2D copy of the next sub-batch.
+#include "edge.cuh"
+#include "hough.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 using namespace cvb;
 
 namespace {
+
+struct PipeSlot {
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evIn = nullptr;       // this slot's upload has landed
+	cvb200_edge_dete canny;
+	cvb200_hough hough;
+	DevBuf in, edges;
+	size_t f0 = 0, nf = 0;            // frames in flight
+	bool busy = false;
+	const uint8_t* dIn = nullptr;     // where the sub-batch's frames are on the device
+	size_t inPitch = 0;
+};
+
 struct PipeState {
-	cudaStream_t sIn = nullptr, sCompute = nullptr;
-	cudaEvent_t evIn[2] = { nullptr, nullptr }, evDone[2] = { nullptr, nullptr };
-	DevBuf in[2], edges; // input chunks are double buffered; the edge maps of the whole batch stay resident for one KHT call
+	std::vector<PipeSlot*> slots;
+	cudaStream_t sCopy = nullptr;
+	cudaEvent_t evStart = nullptr;
 };
 thread_local PipeState t_pipe;
+
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
+
+void copy_params(cvb200_edge_dete& dst, const cvb200_edge_dete& src)
+{
+	dst.id = src.id; dst.tLow = src.tLow; dst.tHigh = src.tHigh; dst.thresholdType = src.thresholdType; dst.taps = src.taps; dst.blur = src.blur;
+	dst.gmaxLanes = src.gmaxLanes; dst.genericKernel = src.genericKernel;
+	if (dst.hystRounds < src.hystRounds) dst.hystRounds = src.hystRounds;
+}
+void copy_params(cvb200_hough& dst, const cvb200_hough& src)
+{
+	dst.id = src.id; dst.rho = src.rho; dst.theta = src.theta; dst.threshold = src.threshold; dst.maxLines = src.maxLines;
+	dst.clusterMinDeviation = src.clusterMinDeviation; dst.clusterMinSize = src.clusterMinSize; dst.kernelMinHeight = src.kernelMinHeight; dst.x86Simd = src.x86Simd;
 }
 
-extern "C" int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride,
+struct Job {
+	cvb200_edge_dete* canny; cvb200_hough* hough;
+	const uint8_t* images; bool onHost;
+	size_t width, height, stride, batch, framePitch;
+	cvb200_hough_line_t* lines; size_t capacity; size_t* counts;
+	size_t frameBytes, sub;
+};
+
+int slot_enqueue(PipeState& st, PipeSlot& s, const Job& j, size_t f0, size_t nf)
+{
+	s.f0 = f0; s.nf = nf;
+	if (j.onHost) {
+		CVB_CHECK(s.in.ensure(j.sub * j.frameBytes));
+		// uploads go through one copy stream in order; the copy may start as soon as this slot's previous kernels are done (finish() has synchronised them)
+		CVB_CUDA(cudaMemcpy2DAsync(s.in.p, j.frameBytes, j.images + f0 * j.framePitch, j.framePitch, j.frameBytes, nf, cudaMemcpyHostToDevice, st.sCopy));
+		CVB_CUDA(cudaEventRecord(s.evIn, st.sCopy));
+		CVB_CUDA(cudaStreamWaitEvent(s.stream, s.evIn, 0));
+		s.dIn = s.in.as<uint8_t>(); s.inPitch = j.frameBytes;
+	}
+	else {
+		CVB_CUDA(cudaStreamWaitEvent(s.stream, st.evStart, 0)); // ordered after what the caller had queued on its stream
+		s.dIn = j.images + f0 * j.framePitch; s.inPitch = j.framePitch;
+	}
+	CVB_CHECK(s.edges.ensure(j.sub * j.frameBytes));
+	CVB_CHECK(edge_enqueue(&s.canny, s.dIn, j.width, j.height, j.stride, s.edges.as<uint8_t>(), nf, s.inPitch, s.stream));
+	CVB_CHECK(kht_enqueue(&s.hough, s.edges.as<uint8_t>(), j.width, j.height, j.stride, nf, j.frameBytes, j.capacity, s.stream));
+	s.busy = true;
+	return CVB200_S_OK;
+}
+
+// waits for the slot, hands its lines out; a sub-batch whose pools were too small / whose hysteresis needed more rounds is simply run again (rare: first call, odd frames)
+int slot_finish(PipeSlot& s, const Job& j)
+{
+	if (!s.busy) return CVB200_S_OK;
+	s.busy = false;
+	for (int attempt = 0; attempt < 16; ++attempt) {
+		bool againE = false, againH = false;
+		CVB_CHECK(edge_finish(&s.canny, &againE));
+		if (!againE) CVB_CHECK(kht_finish(&s.hough, j.lines + s.f0 * j.capacity, j.capacity, j.counts + s.f0, &againH));
+		if (!againE && !againH) return CVB200_S_OK;
+		if (againE) CVB_CHECK(edge_enqueue(&s.canny, s.dIn, j.width, j.height, j.stride, s.edges.as<uint8_t>(), s.nf, s.inPitch, s.stream));
+		CVB_CHECK(kht_enqueue(&s.hough, s.edges.as<uint8_t>(), j.width, j.height, j.stride, s.nf, j.frameBytes, j.capacity, s.stream));
+	}
+	return CVB200_E_INVALID_STATE;
+}
+
+int run_pipeline(Job& j, cudaStream_t callerStream)
+{
+	PipeState& st = t_pipe;
+	if (!st.sCopy) {
+		CVB_CUDA(cudaStreamCreateWithFlags(&st.sCopy, cudaStreamNonBlocking));
+		CVB_CUDA(cudaEventCreateWithFlags(&st.evStart, cudaEventDisableTiming));
+	}
+	j.frameBytes = j.stride * j.height;
+	// sub-batch size: enough frames per linking launch to matter, enough sub-batches to overlap; both tunable for experiments
+	const size_t nSlotsWanted = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SLOTS", 6)));
+	size_t sub = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SUB", 256)));
+	if (sub * 3 > j.batch) sub = std::max<size_t>(1, div_up(j.batch, 3)); // small batches: three sub-batches in flight still overlap the linking latency
+	if (j.batch <= 8) sub = j.batch;                                      // a handful of frames: one sub-batch, no ring
+	j.sub = sub;
+	const size_t nSub = div_up(j.batch, sub);
+	const size_t nSlots = std::min(nSlotsWanted, nSub);
+	while (st.slots.size() < nSlots) {
+		PipeSlot* s = new (std::nothrow) PipeSlot();
+		CVB_REQUIRE(s, CVB200_E_OUT_OF_MEMORY);
+		CVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		CVB_CUDA(cudaEventCreateWithFlags(&s->evIn, cudaEventDisableTiming));
+		s->hough.lastGs = 1.0;
+		st.slots.push_back(s);
+	}
+	for (size_t i = 0; i < nSlots; ++i) { copy_params(st.slots[i]->canny, *j.canny); copy_params(st.slots[i]->hough, *j.hough); st.slots[i]->busy = false; }
+	if (!j.onHost) CVB_CUDA(cudaEventRecord(st.evStart, callerStream));
+	int rc = CVB200_S_OK;
+	for (size_t k = 0; k < nSub && rc == CVB200_S_OK; ++k) {
+		PipeSlot& s = *st.slots[k % nSlots];
+		rc = slot_finish(s, j); // the sub-batch that used this slot nSlots steps ago
+		if (rc == CVB200_S_OK) { const size_t f0 = k * sub; rc = slot_enqueue(st, s, j, f0, std::min(sub, j.batch - f0)); }
+	}
+	// drain in submission order (also on errors: nothing may stay in flight on the cached streams)
+	for (size_t k = 0; k < nSlots; ++k) {
+		PipeSlot& s = *st.slots[(nSub + k) % nSlots];
+		const int r2 = (rc == CVB200_S_OK) ? slot_finish(s, j) : (cudaStreamSynchronize(s.stream), CVB200_S_OK);
+		if (rc == CVB200_S_OK) rc = r2;
+		s.busy = false;
+	}
+	if (rc == CVB200_S_OK) {
+		j.hough->lastGs = st.slots[(nSub - 1) % nSlots]->hough.lastGs;
+		for (size_t i = 0; i < nSlots; ++i) if (j.canny->hystRounds < st.slots[i]->canny.hystRounds) j.canny->hystRounds = st.slots[i]->canny.hystRounds;
+	}
+	return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride,
 	size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts)
 {
 	CVB_REQUIRE_INIT();
 	CVB_REQUIRE(canny && hough && images && counts && width && height && stride >= width && (lines || !capacity), CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(canny->id == CVB200_CANNY_ID && hough->id == CVB200_HOUGHKHT_ID, CVB200_E_INVALID_PARAMETER);
 	if (!batch) return CVB200_S_OK;
 	if (!framePitch) framePitch = stride * height;
 	CVB_REQUIRE(framePitch >= stride * height, CVB200_E_INVALID_PARAMETER);
-	PipeState& st = t_pipe;
-	if (!st.sIn) {
-		CVB_CUDA(cudaStreamCreateWithFlags(&st.sIn, cudaStreamNonBlocking));
-		CVB_CUDA(cudaStreamCreateWithFlags(&st.sCompute, cudaStreamNonBlocking));
-		for (int i = 0; i < 2; ++i) {
-			CVB_CUDA(cudaEventCreateWithFlags(&st.evIn[i], cudaEventDisableTiming));
-			CVB_CUDA(cudaEventCreateWithFlags(&st.evDone[i], cudaEventDisableTiming));
-		}
-	}
-	const size_t frameBytes = stride * height;
-	size_t chunk = (16u << 20) / frameBytes; // ~16 MiB H2D chunks, overlapped with the Canny kernels of the previous chunk
-	if (chunk < 1) chunk = 1;
-	if (chunk > batch) chunk = batch;
-	for (int i = 0; i < 2; ++i) CVB_CHECK(st.in[i].ensure(chunk * frameBytes));
-	CVB_CHECK(st.edges.ensure(batch * frameBytes));
-	const size_t nChunks = div_up(batch, chunk);
-	auto h2d = [&](size_t c) -> int {
-		const int slot = static_cast<int>(c & 1);
-		const size_t f0 = c * chunk, nf = (f0 + chunk <= batch) ? chunk : (batch - f0);
-		if (c >= 2) CVB_CUDA(cudaStreamWaitEvent(st.sIn, st.evDone[slot], 0));
-		CVB_CUDA(cudaMemcpy2DAsync(st.in[slot].p, frameBytes, images + f0 * framePitch, framePitch, frameBytes, nf, cudaMemcpyHostToDevice, st.sIn));
-		CVB_CUDA(cudaEventRecord(st.evIn[slot], st.sIn));
-		return CVB200_S_OK;
-	};
-	CVB_CHECK(h2d(0));
-	for (size_t c = 0; c < nChunks; ++c) {
-		const int slot = static_cast<int>(c & 1);
-		const size_t f0 = c * chunk, nf = (f0 + chunk <= batch) ? chunk : (batch - f0);
-		if (c + 1 < nChunks) CVB_CHECK(h2d(c + 1));
-		CVB_CUDA(cudaStreamWaitEvent(st.sCompute, st.evIn[slot], 0));
-		CVB_CHECK(cvb200_edge_dete_process_dev(canny, st.in[slot].as<uint8_t>(), width, height, stride, st.edges.as<uint8_t>() + f0 * frameBytes, nf, frameBytes,
-			reinterpret_cast<cvb200_stream_t>(st.sCompute)));
-		CVB_CUDA(cudaEventRecord(st.evDone[slot], st.sCompute));
-	}
-	// the linking stage is latency bound with one warp per frame: its launch time does not depend on the number of frames, so the whole batch goes in one call
-	CVB_CHECK(cvb200_hough_process_dev(hough, st.edges.as<uint8_t>(), width, height, stride, batch, frameBytes, lines, capacity, counts, reinterpret_cast<cvb200_stream_t>(st.sCompute)));
-	CVB_CUDA(cudaStreamSynchronize(st.sCompute));
-	return CVB200_S_OK;
+	std::lock_guard<std::mutex> l1(canny->mutex);
+	std::lock_guard<std::mutex> l2(hough->mutex);
+	Job j = { canny, hough, images, true, width, height, stride, batch, framePitch, lines, capacity, counts, 0, 0 };
+	return run_pipeline(j, nullptr);
 }
+
+int cvb200_canny_kht_process_batch_dev(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride,
+	size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cvb200_stream_t stream)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(canny && hough && images && counts && width && height && stride >= width && (lines || !capacity), CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(canny->id == CVB200_CANNY_ID && hough->id == CVB200_HOUGHKHT_ID, CVB200_E_INVALID_PARAMETER);
+	if (!batch) return CVB200_S_OK;
+	if (!framePitch) framePitch = stride * height;
+	CVB_REQUIRE(framePitch >= stride * height, CVB200_E_INVALID_PARAMETER);
+	std::lock_guard<std::mutex> l1(canny->mutex);
+	std::lock_guard<std::mutex> l2(hough->mutex);
+	Job j = { canny, hough, images, false, width, height, stride, batch, framePitch, lines, capacity, counts, 0, 0 };
+	return run_pipeline(j, as_stream(stream));
+}
+
+} // extern "C"

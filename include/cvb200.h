@@ -250,8 +250,8 @@ CVB200_API int cvb200_hough_set(cvb200_hough_t* hough, int id, const void* value
 CVB200_API int cvb200_hough_get(cvb200_hough_t* hough, int id, void* valuePtr, size_t valueSize);
 /* Host edge map (non-zero = edge) in; lines out, strongest first (the reference's order). *count = lines found (<= maxLines); at most `capacity` written. Synchronous. */
 CVB200_API int cvb200_hough_process(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t height, size_t stride, cvb200_hough_line_t* lines, size_t capacity, size_t* count);
-/* Device edge maps (batch) in; lines[frame*capacity + k] and counts[frame] are HOST arrays (the final peak ordering is the reference's std::sort + sweep,
- * run on the host on a few thousand accumulator cells). Synchronous. */
+/* Device edge maps (batch) in; lines[frame*capacity + k] and counts[frame] are HOST arrays. Everything, including the reference's std::sort tie order and the
+ * sweep of the peak stage, runs on the device; the call returns when the lines are in host memory. */
 CVB200_API int cvb200_hough_process_dev(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cvb200_stream_t stream);
 
 /* ================================================================================================
@@ -366,6 +366,10 @@ CVB200_API int cvb200_morph_process_dev(const uint8_t* in, size_t width, size_t 
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
 CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);
+/* Same pipeline on frames that are already in device memory (`images` is a device pointer; `lines` / `counts` are host arrays). The work is ordered after what was
+ * queued on `stream` before the call; the call returns when the lines are in host memory. Sub-batches of the frames run on several internal streams so that the
+ * linking stage of one sub-batch overlaps the other stages of its neighbours (environment: CVB200_PIPE_SUB frames per sub-batch, CVB200_PIPE_SLOTS in flight). */
+CVB200_API int cvb200_canny_kht_process_batch_dev(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cvb200_stream_t stream);
 
 #ifdef __cplusplus
 }

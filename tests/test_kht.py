@@ -176,3 +176,61 @@ def test_cuda_canny_kht_host_batch_many_chunks(cvb):
             want, gs_last = oracle.hough_kht("orc", canny_edges(frames[k]), 1.0, 1.0, 30)
             same_lines(got[k], want)
         assert kht.getFloat64(_ffi.HOUGHKHT_GET_FLT64_GS) == gs_last
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sub,slots", [(4, 2), (7, 3), (256, 6)])
+def test_cuda_canny_kht_device_pipeline_ring(cvb, sub, slots, monkeypatch):
+    """cvb200_canny_kht_process_batch_dev: sub-batches on a ring of slots (each slot a private copy of the two detectors), slots reused several times,
+    last sub-batch ragged; every frame's lines must be the oracle's, whatever the cut."""
+    import torch
+    from compv_b200 import _ffi
+    monkeypatch.setenv("CVB200_PIPE_SUB", str(sub))
+    monkeypatch.setenv("CVB200_PIPE_SLOTS", str(slots))
+    w, h, batch = 320, 200, 23
+    frames = np.stack([frame_g(w, h, 900 + k) if k % 3 else frame_smooth(w, h, k) for k in range(batch)])
+    d_in = torch.from_numpy(frames).cuda()
+    canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
+    canny.set_preblur(5, 1.0)
+    kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 30)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        got = cvb.canny_kht_process_batch_dev(canny, kht, d_in, w, h, w, batch, stream=stream)
+        gs_last = None
+        for k in range(batch):
+            want, gs_last = oracle.hough_kht("orc", canny_edges(frames[k]), 1.0, 1.0, 30)
+            same_lines(got[k], want)
+        assert kht.getFloat64(_ffi.HOUGHKHT_GET_FLT64_GS) == gs_last
+
+
+@pytest.mark.gpu
+def test_cuda_kht_pools_grow_on_overflow(cvb):
+    """The pools are sized from earlier calls: a first small call followed by a dense frame (every pool too small) must still give the oracle's lines."""
+    from compv_b200 import _ffi
+    d = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 1)
+    small = np.zeros((48, 64), np.uint8); small[20, 5:40] = 255
+    same_lines(d.process(small), oracle.hough_kht("orc", small, 1.0, 1.0, 1)[0])
+    dense = canny_edges(frame_uniform(640, 480, 5), blur=False)
+    same_lines(d.process(dense), oracle.hough_kht("orc", dense, 1.0, 1.0, 1)[0])
+
+
+@pytest.mark.gpu
+def test_cuda_canny_hysteresis_needs_many_rounds(cvb):
+    """A weak edge snaking through many 64x64 tiles with a single strong pixel at one end: the closure needs more list-driven rounds than one call issues,
+    the detector must notice, raise its round count and still return the reference's edge map."""
+    from compv_b200 import _ffi
+    w, h = 1024, 320
+    img = np.full((h, w), 20, np.uint8)
+    # a low-contrast ridge (weak after NMS) across the whole width, alternating rows joined at the ends ...
+    rows = list(range(20, h - 20, 24))
+    for i, r in enumerate(rows):
+        img[r, 10:w - 10] = 60
+        x = w - 11 if i % 2 == 0 else 10
+        if i + 1 < len(rows):
+            img[r:rows[i + 1] + 1, x] = 60
+    img[rows[0], 10:14] = 255              # ... and one strong seed at its beginning
+    canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 30.0, 400.0, 3)
+    got = canny.process(img)
+    want = oracle.edge_dete("orc", img, "canny", 30.0, 400.0, 3)
+    assert np.array_equal(got, want)
+    assert (want == 255).sum() > 2000       # the closure really travelled
