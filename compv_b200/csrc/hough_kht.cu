@@ -56,7 +56,6 @@ struct KhtFrame {           // per-frame offsets into the batch-wide pools + dev
 struct KhtStack { unsigned int a, b, mi, nclus0; double ratio, ratioLeft; unsigned int state, pad; };
 
 // ---- bitmap -------------------------------------------------------------------------------------
-template <bool REV>
 __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int* __restrict__ bits, KhtGeom g, unsigned int* edgeCount)
 {
 	const int frame = blockIdx.z, y = blockIdx.y;
@@ -77,7 +76,7 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 		else {
 			for (int j = 0; j < 32 && x0 + j < g.W; ++j) if (row[x0 + j]) word |= 1u << j;
 		}
-		bits[(static_cast<size_t>(frame) * (g.H + 2 * KHT_PADR) + y + KHT_PADR) * g.WW + wi + 1] = REV ? __brev(word) : word;
+		bits[(static_cast<size_t>(frame) * (g.H + 2 * KHT_PADR) + y + KHT_PADR) * g.WW + wi + 1] = __brev(word); // bit 31 = leftmost column (kht_walk.cuh)
 	}
 	unsigned int c = __popc(word);
 	for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -89,7 +88,6 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 // One warp per frame: the 32 lanes find the next seed in raster order (32 bitmap words per ballot), lane 0 runs Algorithm 5 for it.  The first walk of a
 // string is stored in walk order; the reversal the reference applies (std::reverse, houghkht.cxx:752-755) is left to kht_reverse_kernel, which is parallel
 // over strings, instead of a load-after-store round trip through L2 between two walks.
-template <bool REV, bool BF>
 __global__ void __launch_bounds__(32)
 kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll,
 	unsigned int* __restrict__ revAll, KhtFrame* frames, KhtGeom g)
@@ -102,6 +100,10 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointe
 	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff); // ushort2 {x, y} written as x | y << 16
 	uint2* strings = stringsAll + fr.strOff;
 	unsigned int* revs = revAll + fr.strOff;
+	// the walker forms every address as pointer + 32-bit offset: keep the two pointers in registers (otherwise they are re-derived from the kernel parameters
+	// with four 64-bit instructions and a constant-bank load per access)
+	asm volatile("" : "+l"(base));
+	asm volatile("" : "+l"(poss));
 	unsigned int nPos = 0, nStr = 0; // meaningful on lane 0
 	const int lastWord = (W - 1) >> 5;
 
@@ -122,16 +124,16 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointe
 				const int wi = wb + lane;
 				unsigned int w = (wi <= lastWord) ? row[wi] : 0u; // plain load: served by this SM's L1, which the walker's stores keep current
 				// seeds are interior columns only: x in [1, W-2]
-				if (wi == 0) w &= ~kw_colbit<REV>(0);
-				if (wi == lastWord) w &= ~kw_colbit<REV>((W - 1) & 31);
+				if (wi == 0) w &= ~kw_colbit(0);
+				if (wi == lastWord) w &= ~kw_colbit((W - 1) & 31);
 				const unsigned int any = __ballot_sync(0xffffffffu, w != 0);
 				if (!any) break;
 				const int src = __ffs(any) - 1;
 				const unsigned int sw = __shfl_sync(0xffffffffu, w, src);
 				if (lane == 0) {
-					const int xr = (wb + src) * 32 + kw_first_col<REV>(sw);
+					const int xr = (wb + src) * 32 + kw_first_col(sw);
 					unsigned int rev;
-					const unsigned int n = kht_link_string<REV, BF>(base, WW, static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16), poss + nPos, &rev);
+					const unsigned int n = kht_link_string(base, WW, static_cast<unsigned int>(xr) | (static_cast<unsigned int>(y) << 16), poss + nPos, &rev);
 					if (n >= g.minSize) {
 						strings[nStr] = make_uint2(nPos, nPos + n);
 						revs[nStr] = rev;
@@ -842,14 +844,14 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 		dim3 grid(static_cast<unsigned>(div_up(g.WW, 64)), static_cast<unsigned>(g.H), B);
 		CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 		KernelScope ks_("kht_bits", stream);
-		kht_bits_kernel<true><<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, dEdgeCount);
+		kht_bits_kernel<<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, dEdgeCount);
 	}
 	CVB_LAUNCHED();
 	{ KernelScope ks_("kht_offsets", stream);
 	  kht_offsets1_kernel<<<1, 256, 0, stream>>>(dEdgeCount, dFrames, dMeta, static_cast<int>(batch), g.minSize, h->posCapEl, h->strCapEl); }
 	CVB_LAUNCHED();
 	{ KernelScope ks_("kht_link", stream);
-	  kht_link_kernel<true, false><<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g); }
+	  kht_link_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g); }
 	CVB_LAUNCHED();
 	{ KernelScope ks_("kht_reverse", stream);
 	  kht_reverse_kernel<<<dim3(8, B), 128, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames); }

@@ -9,8 +9,10 @@
 //     load of the row after it has a whole step to arrive;
 //   * the 8-neighbourhood is gathered with three rotates + three ANDs + one OR into bit fields 8 apart (row | row << 8 | row << 16) so that ONE
 //     find-first-set gives the reference's priority order (TL, T, TR, L, R, BL, B, BR) and the move decodes as k & 3, k >> 3;
-//   * REV = the bitmap words are bit-reversed (bit 31 = leftmost column) and the TOP row goes to the HIGH field: the priority encoder is then a single
-//     find-leading-one (FLO) instead of bit-reverse + FLO.
+//   * the bitmap words are bit-reversed (bit 31 = leftmost column) and the TOP row goes to the HIGH field: the priority encoder is then a single
+//     find-leading-one (FLO) instead of bit-reverse + FLO;
+//   * every load has a whole step between its issue and its first use (the machine is in-order: a consumer placed right behind its load stalls the chain
+//     for the full L1 / L2 latency, which is what ncu showed for the first version of this walker).
 #pragma once
 #include <stdint.h>
 
@@ -68,24 +70,39 @@ KW_FN int kw_highest(unsigned int v) // index of the highest set bit, v != 0
 #endif
 }
 
-// bit of column j (0..31) inside a bitmap word
-template <bool REV> KW_FN unsigned int kw_colbit(int j) { return REV ? (0x80000000u >> j) : (1u << j); }
-// column (0..31) of the first pixel, in raster order, of a non-zero word
-template <bool REV> KW_FN int kw_first_col(unsigned int w) { return REV ? (31 - kw_highest(w)) : kw_lowest(w); }
+// Bitmap words are stored bit-reversed: bit 31 = leftmost of the word's 32 columns, so that "first in raster order" and "highest priority" are both
+// "highest set bit" (one FLO instruction).
+KW_FN unsigned int kw_colbit(int j) { return 0x80000000u >> j; }              // bit of column j (0..31) inside a bitmap word
+KW_FN int kw_first_col(unsigned int w) { return 31 - kw_highest(w); }         // column of the first pixel, in raster order, of a non-zero word
 
-// BF = the row rotation of a vertical move is done with selects instead of branches
-template <bool REV, bool BF>
+KW_FN void kw_prefetch_l1(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+	(void)p;
+#endif
+}
+
+#define KHT_WALK_PREFETCH_ROWS 6 // a vertical move prefetches the row this many rows further on into L1: the far-row load two steps later then hits
+
+// The walker's state.  Window index i (0..31) <-> bit 31 - i; the current pixel sits at bit q = c + 1, c kept in [0, 29].
+// The three rows of the 8-neighbourhood are held PRE-ROTATED (T = row(y-1) rotated by 16, M = row(y) rotated left by 8, B = row(y+1) as is) so that one
+// rotation count c brings the three 3-bit fields to bits 16-18 / 8-10 / 0-2: top row in the high field, left neighbour in the high bit of each field.
 struct KhtWalker {
-	unsigned int r0, r1, r2, r3, r4; // rows y-2 .. y+2, 32 columns from padded column c0 (window index i <-> bit i, or bit 31 - i when REV)
-	int qa, qb, qc;                  // q - 1, q - 9, q - 17 where q = bit of the current pixel, kept in [1, 30]: the three rotation counts
+	unsigned int T, M, B;            // rows y-1, y, y+1 (pre-rotated, see above)
+	unsigned int Fu, Fd;             // rows y-2, y+2 (not rotated)
+	unsigned int plo, phi; int pend; // a far row still in flight: raw words, 1 = it is Fu, 2 = it is Fd, 0 = none.  Consumed one step later at the earliest,
+	                                 // so that the load's latency is off the dependency chain
+	int c;                           // rotation count = bit of the current pixel - 1
 	int ro;                          // word offset of padded word 0 of row y from `base`
-	int w0, s;                       // c0 = 32 * w0 + s
+	int w0, s;                       // the window starts at padded column 32 * w0 + s
 	unsigned int xy;                 // x | y << 16 (image coordinates): the value that is stored as the position
 
 	KW_FN unsigned int load_row(const unsigned int* base, int off) const
 	{
 		const unsigned int* row = base + (off + w0);
-		return REV ? kw_funnel_l(row[1], row[0], s) : kw_funnel_r(row[0], row[1], s);
+		return kw_funnel_l(row[1], row[0], s);
 	}
 	// (re)load the window with the current pixel in the middle; `base` = padded word 0 of image row 0
 	KW_FN void centre(const unsigned int* base, int WW)
@@ -94,65 +111,59 @@ struct KhtWalker {
 		const int c0 = X - 16;
 		w0 = c0 >> 5; s = c0 & 31;
 		ro = y * WW;
-		r0 = load_row(base, ro - 2 * WW); r1 = load_row(base, ro - WW); r2 = load_row(base, ro); r3 = load_row(base, ro + WW); r4 = load_row(base, ro + 2 * WW);
-		const int q = REV ? 15 : 16;
-		qa = q - 1; qb = q - 9; qc = q - 17;
+		Fu = load_row(base, ro - 2 * WW);
+		T = kw_rotr(load_row(base, ro - WW), 16);
+		M = kw_rotr(load_row(base, ro), 24);
+		B = load_row(base, ro + WW);
+		Fd = load_row(base, ro + 2 * WW);
+		pend = 0; plo = 0; phi = 0;
+		c = 14; // window index 16 <-> bit 15
 	}
 	// Erase the current pixel (window + memory), then Algorithm 6: move to the first remaining neighbour in the order TL, T, TR, L, R, BL, B, BR.
-	// false when there is none.  The centre bit is masked out of the neighbourhood instead of waiting for the erase, so the erase is off the chain.
+	// false when there is none.  The memory erase is a read-modify-write of one bitmap word: the read is issued first and the write last, with the whole
+	// step in between, and the centre bit is masked out of the neighbourhood instead of waiting for the erase of M.
 	KW_FN bool step(unsigned int* base, int WW)
 	{
-		unsigned int m;
-		if (REV) m = (kw_rotr(r1, qc) & 0x70000u) | (kw_rotr(r2, qb) & 0x500u) | (kw_rotr(r3, qa) & 7u);
-		else m = (kw_rotr(r1, qa) & 7u) | (kw_rotr(r2, qb) & 0x500u) | (kw_rotr(r3, qc) & 0x70000u);
-		r2 &= ~(2u << qa);
-		{
-			const int X = static_cast<int>(xy & 0xffffu) + 32;
-			unsigned int* wp = base + (ro + (X >> 5));
-			*wp &= ~kw_colbit<REV>(X & 31);
+		const int X = static_cast<int>(xy & 0xffffu) + 32;
+		unsigned int* wp = base + (ro + (X >> 5));
+		const unsigned int old = *wp;
+		const unsigned int keep = ~kw_colbit(X & 31);
+		const unsigned int m = (kw_rotr(T, c) & 0x70000u) | (kw_rotr(M, c) & 0x500u) | (kw_rotr(B, c) & 7u);
+		M &= ~kw_rotr(0x200u, 32 - c); // bit c + 1 of row y sits at bit c + 9 of M
+		if (!m) { *wp = old & keep; return false; }
+		const int k = kw_highest(m);
+		const int kx = k & 3, ky = k >> 3;   // kx: 2 = left, 1 = same column, 0 = right;  ky: 2 = up, 1 = same row, 0 = down
+		c += kx - 1;
+		xy += static_cast<unsigned int>(65537 - kx - (ky << 16));
+		if (static_cast<unsigned int>(c) > 29u) { *wp = old & keep; centre(base, WW); return true; } // left the window sideways: the reload must see the erase
+		if (ky != 1) {
+			// the far row that was requested by the previous vertical move (at least one step ago) is taken out of its raw words now
+			const unsigned int v = kw_funnel_l(phi, plo, s);
+			if (pend == 1) Fu = v;
+			if (pend == 2) Fd = v;
+			int far;
+			if (ky == 2) { ro -= WW; Fd = B; B = kw_rotr(M, 8); M = kw_rotr(T, 8); T = kw_rotr(Fu, 16); far = ro - 2 * WW; pend = 1; kw_prefetch_l1(base + (ro - KHT_WALK_PREFETCH_ROWS * WW + w0)); }
+			else { ro += WW; Fu = kw_rotr(T, 16); T = kw_rotr(M, 24); M = kw_rotr(B, 24); B = Fd; far = ro + 2 * WW; pend = 2; kw_prefetch_l1(base + (ro + KHT_WALK_PREFETCH_ROWS * WW + w0)); }
+			const unsigned int* row = base + (far + w0);
+			plo = row[0]; phi = row[1];
 		}
-		if (!m) return false;
-		const int k = REV ? kw_highest(m) : kw_lowest(m);
-		const int kx = k & 3, ky = k >> 3;   // 0..2 each
-		qa += kx - 1; qb += kx - 1; qc += kx - 1;
-		// x moves with the bit index (or against it when REV); y moves down when the field is the bottom one
-		xy += REV ? static_cast<unsigned int>(65537 - kx - (ky << 16)) : static_cast<unsigned int>(kx + (ky << 16) - 65537);
-		if (static_cast<unsigned int>(qa) > 29u) { centre(base, WW); return true; }
-		const int up = REV ? 2 : 0;
-		if (BF) {
-			const bool isUp = (ky == up), isDn = (ky == 2 - up);
-			const int dro = isUp ? -WW : (isDn ? WW : 0);
-			ro += dro;
-			const unsigned int n0 = r0, n1 = r1, n2 = r2, n3 = r3, n4 = r4;
-			unsigned int far = 0;
-			if (ky != 1) far = load_row(base, ro + 2 * dro);
-			r0 = isUp ? far : (isDn ? n1 : n0);
-			r1 = isUp ? n0 : (isDn ? n2 : n1);
-			r2 = isUp ? n1 : (isDn ? n3 : n2);
-			r3 = isUp ? n2 : (isDn ? n4 : n3);
-			r4 = isUp ? n3 : (isDn ? far : n4);
-		}
-		else {
-			if (ky == up) { ro -= WW; r4 = r3; r3 = r2; r2 = r1; r1 = r0; r0 = load_row(base, ro - 2 * WW); }
-			else if (ky == 2 - up) { ro += WW; r0 = r1; r1 = r2; r2 = r3; r3 = r4; r4 = load_row(base, ro + 2 * WW); }
-		}
+		*wp = old & keep;
 		return true;
 	}
 };
 
 // Algorithm 5 for one seed: appends the string's positions at `out` (first walk in walk order -- the caller reverses out[0, rev) afterwards, the
 // reference's std::reverse, houghkht.cxx:752-755 -- then the second walk) and returns the number of positions; *rev = length of the first walk.
-template <bool REV, bool BF>
 KW_FN unsigned int kht_link_string(unsigned int* base, int WW, unsigned int seedXY, unsigned int* out, unsigned int* rev)
 {
-	unsigned int n = 0;
-	KhtWalker<REV, BF> wk;
+	int n = 0; // a signed 32-bit index: one IMAD.WIDE per address
+	KhtWalker wk;
 	wk.xy = seedXY;
 	wk.centre(base, WW);
 	do {
 		out[n++] = wk.xy;
 	} while (wk.step(base, WW));
-	*rev = n;
+	*rev = static_cast<unsigned int>(n);
 	wk.xy = seedXY;
 	wk.centre(base, WW);
 	if (wk.step(base, WW)) { // the seed is erased already: this only looks for what the first walk left around it
@@ -160,7 +171,7 @@ KW_FN unsigned int kht_link_string(unsigned int* base, int WW, unsigned int seed
 			out[n++] = wk.xy;
 		} while (wk.step(base, WW));
 	}
-	return n;
+	return static_cast<unsigned int>(n);
 }
 
 } // namespace cvb

@@ -103,11 +103,14 @@ int run_pipeline(Job& j, cudaStream_t callerStream)
 		CVB_CUDA(cudaEventCreateWithFlags(&st.evStart, cudaEventDisableTiming));
 	}
 	j.frameBytes = j.stride * j.height;
-	// sub-batch size: enough frames per linking launch to matter, enough sub-batches to overlap; both tunable for experiments
+	// Sub-batches.  The linking kernel's duration hardly depends on how many frames it holds, and a slot's chain is Canny -> linking -> voting/peaks:
+	//   * device frames: as many sub-batches as slots, all enqueued at once (a slot that has to be waited for and refilled leaves the GPU idle for one linking latency);
+	//   * host frames: the upload paces everything, so a ring of smaller sub-batches keeps the tail (the last sub-batch's chain after its upload) short.
 	const size_t nSlotsWanted = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SLOTS", 6)));
-	size_t sub = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SUB", 256)));
-	if (sub * 3 > j.batch) sub = std::max<size_t>(1, div_up(j.batch, 3)); // small batches: three sub-batches in flight still overlap the linking latency
-	if (j.batch <= 8) sub = j.batch;                                      // a handful of frames: one sub-batch, no ring
+	size_t sub;
+	if (j.batch <= 8) sub = j.batch; // a handful of frames: one sub-batch, no ring
+	else if (j.onHost) { sub = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SUB", 128))); if (sub * 3 > j.batch) sub = std::max<size_t>(1, div_up(j.batch, 3)); }
+	else { const int forced = env_int("CVB200_PIPE_SUB", 0); sub = forced > 0 ? static_cast<size_t>(forced) : std::max<size_t>(div_up(j.batch, nSlotsWanted), std::min<size_t>(j.batch, 16)); }
 	j.sub = sub;
 	const size_t nSub = div_up(j.batch, sub);
 	const size_t nSlots = std::min(nSlotsWanted, nSub);
