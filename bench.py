@@ -24,6 +24,10 @@ import sys
 import threading
 import time
 
+# The pipeline keeps several sub-batches in flight on their own streams; with the default of 8 hardware work queues the driver aliases streams onto
+# shared queues and serialises them (measured: slots 4 and 5 of 6 only started when slots 0 and 1 had finished).  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -37,6 +37,12 @@ struct KernelScope {
 	~KernelScope() { if (on) profile_mark(name, stream, false); }
 };
 
+// Timeline tracing for pipeline tuning (environment CVB200_TRACE=1): trace_mark records an event on `stream` under `tag`; trace_dump (after a device
+// synchronisation) prints every mark's time relative to the first one and forgets them.  Costs one getenv-cached flag test when off.
+bool trace_on();
+void trace_mark(cudaStream_t stream, const char* tag, int slot);
+void trace_dump(const char* title);
+
 // Grow-only device scratch buffer (the reference caches its scratch per object the same way, e.g. canny_dete.cxx:133-147)
 struct DevBuf {
 	void* p = nullptr;

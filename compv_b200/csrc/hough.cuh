@@ -15,6 +15,7 @@ struct cvb200_hough {
 	cvb::HostBuf hTabs;
 	size_t posCapEl = 0, strCapEl = 0, voteCapEl = 0;   // element capacities of the shared pools (grow-only)
 	double tabRho = 0, tabTheta = 0, tabR = 0; size_t tabNRho = 0;
+	int traceSlot = 0;
 	size_t pendBatch = 0, pendCapacity = 0; cudaStream_t pendStream = nullptr; // what kht_enqueue left for kht_finish
 	cvb::DevBuf bits, poss, strings, strRev, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
 	cvb::HostBuf hFrames, hVotes, hCounts;

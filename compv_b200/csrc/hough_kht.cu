@@ -850,9 +850,11 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	{ KernelScope ks_("kht_offsets", stream);
 	  kht_offsets1_kernel<<<1, 256, 0, stream>>>(dEdgeCount, dFrames, dMeta, static_cast<int>(batch), g.minSize, h->posCapEl, h->strCapEl); }
 	CVB_LAUNCHED();
+	trace_mark(stream, "link>", h->traceSlot);
 	{ KernelScope ks_("kht_link", stream);
 	  kht_link_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g); }
 	CVB_LAUNCHED();
+	trace_mark(stream, "link<", h->traceSlot);
 	{ KernelScope ks_("kht_reverse", stream);
 	  kht_reverse_kernel<<<dim3(8, B), 128, 0, stream>>>(h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames); }
 	CVB_LAUNCHED();

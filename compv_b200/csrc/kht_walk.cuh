@@ -86,7 +86,10 @@ KW_FN void kw_prefetch_l1(const void* p)
 
 #define KHT_WALK_PREFETCH_ROWS 6 // a vertical move prefetches the row this many rows further on into L1: the far-row load two steps later then hits
 
-// The walker's state.  Window index i (0..31) <-> bit 31 - i; the current pixel sits at bit q = c + 1, c kept in [0, 29].
+// The walker's state.  Window index i (0..31) <-> bit 31 - i; the current pixel sits at bit q = c + 1, c kept in [6, 23] (window index 7..24) so that the
+// aligned 8-column byte that holds the pixel always lies inside the window: the memory erase is then ONE BYTE STORE taken from the window row, with no load.
+// (ncu on the first two versions: a read-modify-write of the bitmap word costs an L2 round trip per step, because the previous step's store has just
+// invalidated that line in L1 -- every version that loaded before storing ran at the same ~300 cycles per pixel whatever else it did.)
 // The three rows of the 8-neighbourhood are held PRE-ROTATED (T = row(y-1) rotated by 16, M = row(y) rotated left by 8, B = row(y+1) as is) so that one
 // rotation count c brings the three 3-bit fields to bits 16-18 / 8-10 / 0-2: top row in the high field, left neighbour in the high bit of each field.
 struct KhtWalker {
@@ -104,11 +107,11 @@ struct KhtWalker {
 		const unsigned int* row = base + (off + w0);
 		return kw_funnel_l(row[1], row[0], s);
 	}
-	// (re)load the window with the current pixel in the middle; `base` = padded word 0 of image row 0
-	KW_FN void centre(const unsigned int* base, int WW)
+	// (re)load the window with the current pixel at window index ip (7..24); `base` = padded word 0 of image row 0
+	KW_FN void centre(const unsigned int* base, int WW, int ip)
 	{
 		const int X = static_cast<int>(xy & 0xffffu) + 32, y = static_cast<int>(xy >> 16);
-		const int c0 = X - 16;
+		const int c0 = X - ip;
 		w0 = c0 >> 5; s = c0 & 31;
 		ro = y * WW;
 		Fu = load_row(base, ro - 2 * WW);
@@ -117,25 +120,27 @@ struct KhtWalker {
 		B = load_row(base, ro + WW);
 		Fd = load_row(base, ro + 2 * WW);
 		pend = 0; plo = 0; phi = 0;
-		c = 14; // window index 16 <-> bit 15
+		c = 30 - ip;
 	}
 	// Erase the current pixel (window + memory), then Algorithm 6: move to the first remaining neighbour in the order TL, T, TR, L, R, BL, B, BR.
-	// false when there is none.  The memory erase is a read-modify-write of one bitmap word: the read is issued first and the write last, with the whole
-	// step in between, and the centre bit is masked out of the neighbourhood instead of waiting for the erase of M.
+	// false when there is none.
 	KW_FN bool step(unsigned int* base, int WW)
 	{
-		const int X = static_cast<int>(xy & 0xffffu) + 32;
-		unsigned int* wp = base + (ro + (X >> 5));
-		const unsigned int old = *wp;
-		const unsigned int keep = ~kw_colbit(X & 31);
-		const unsigned int m = (kw_rotr(T, c) & 0x70000u) | (kw_rotr(M, c) & 0x500u) | (kw_rotr(B, c) & 7u);
+		const unsigned int m = (kw_rotr(T, c) & 0x70000u) | (kw_rotr(M, c) & 0x500u) | (kw_rotr(B, c) & 7u); // the centre bit is masked out: no need to wait for the erase
 		M &= ~kw_rotr(0x200u, 32 - c); // bit c + 1 of row y sits at bit c + 9 of M
-		if (!m) { *wp = old & keep; return false; }
+		{
+			// the aligned byte (8 columns) that holds the pixel, taken from the erased window row: column X & ~7 is its bit 7.  Bitmap words are bit-reversed,
+			// so inside a little-endian word the byte of columns 8k..8k+7 is byte 3 - k.
+			const int X = static_cast<int>(xy & 0xffffu) + 32;
+			const unsigned int v = kw_rotr(M, c + (X & 7) + 2);
+			reinterpret_cast<unsigned char*>(base + ro)[(X >> 3) ^ 3] = static_cast<unsigned char>(v);
+		}
+		if (!m) return false;
 		const int k = kw_highest(m);
 		const int kx = k & 3, ky = k >> 3;   // kx: 2 = left, 1 = same column, 0 = right;  ky: 2 = up, 1 = same row, 0 = down
 		c += kx - 1;
 		xy += static_cast<unsigned int>(65537 - kx - (ky << 16));
-		if (static_cast<unsigned int>(c) > 29u) { *wp = old & keep; centre(base, WW); return true; } // left the window sideways: the reload must see the erase
+		if (static_cast<unsigned int>(c - 6) > 17u) { centre(base, WW, c < 6 ? 9 : 22); return true; } // left the window sideways: re-enter it with room ahead in the direction of travel
 		if (ky != 1) {
 			// the far row that was requested by the previous vertical move (at least one step ago) is taken out of its raw words now
 			const unsigned int v = kw_funnel_l(phi, plo, s);
@@ -147,7 +152,6 @@ struct KhtWalker {
 			const unsigned int* row = base + (far + w0);
 			plo = row[0]; phi = row[1];
 		}
-		*wp = old & keep;
 		return true;
 	}
 };
@@ -159,13 +163,13 @@ KW_FN unsigned int kht_link_string(unsigned int* base, int WW, unsigned int seed
 	int n = 0; // a signed 32-bit index: one IMAD.WIDE per address
 	KhtWalker wk;
 	wk.xy = seedXY;
-	wk.centre(base, WW);
+	wk.centre(base, WW, 12); // a seed is the raster-first pixel left: nothing above it or to its left, the walk starts rightwards or downwards
 	do {
 		out[n++] = wk.xy;
 	} while (wk.step(base, WW));
 	*rev = static_cast<unsigned int>(n);
 	wk.xy = seedXY;
-	wk.centre(base, WW);
+	wk.centre(base, WW, 16);
 	if (wk.step(base, WW)) { // the seed is erased already: this only looks for what the first walk left around it
 		do {
 			out[n++] = wk.xy;

@@ -73,8 +73,13 @@ int slot_enqueue(PipeState& st, PipeSlot& s, const Job& j, size_t f0, size_t nf)
 		s.dIn = j.images + f0 * j.framePitch; s.inPitch = j.framePitch;
 	}
 	CVB_CHECK(s.edges.ensure(j.sub * j.frameBytes));
+	const int slotId = static_cast<int>(f0 / j.sub);
+	trace_mark(s.stream, "canny>", slotId);
 	CVB_CHECK(edge_enqueue(&s.canny, s.dIn, j.width, j.height, j.stride, s.edges.as<uint8_t>(), nf, s.inPitch, s.stream));
+	trace_mark(s.stream, "canny<", slotId);
+	s.hough.traceSlot = slotId;
 	CVB_CHECK(kht_enqueue(&s.hough, s.edges.as<uint8_t>(), j.width, j.height, j.stride, nf, j.frameBytes, j.capacity, s.stream));
+	trace_mark(s.stream, "kht<", slotId);
 	s.busy = true;
 	return CVB200_S_OK;
 }
@@ -137,6 +142,7 @@ int run_pipeline(Job& j, cudaStream_t callerStream)
 		if (rc == CVB200_S_OK) rc = r2;
 		s.busy = false;
 	}
+	trace_dump(j.onHost ? "canny+kht pipeline, host frames" : "canny+kht pipeline, device frames");
 	if (rc == CVB200_S_OK) {
 		j.hough->lastGs = st.slots[(nSub - 1) % nSlots]->hough.lastGs;
 		for (size_t i = 0; i < nSlots; ++i) if (j.canny->hystRounds < st.slots[i]->canny.hystRounds) j.canny->hystRounds = st.slots[i]->canny.hystRounds;

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,6 +65,36 @@ void profile_mark(const char* name, cudaStream_t stream, bool begin)
 	}
 }
 
+// ---- timeline tracing ----
+struct TraceRec { const char* tag; int slot; cudaEvent_t ev; };
+static std::vector<TraceRec> g_trace;
+static std::mutex g_trace_mutex;
+bool trace_on() { static const bool on = getenv("CVB200_TRACE") != nullptr; return on; }
+void trace_mark(cudaStream_t stream, const char* tag, int slot)
+{
+	if (!trace_on()) return;
+	TraceRec r; r.tag = tag; r.slot = slot; r.ev = nullptr;
+	cudaEventCreate(&r.ev);
+	cudaEventRecord(r.ev, stream);
+	std::lock_guard<std::mutex> lock(g_trace_mutex);
+	g_trace.push_back(r);
+}
+void trace_dump(const char* title)
+{
+	if (!trace_on()) return;
+	cudaDeviceSynchronize();
+	std::lock_guard<std::mutex> lock(g_trace_mutex);
+	if (g_trace.empty()) return;
+	fprintf(stderr, "[cvb200 trace] %s\n", title);
+	for (auto& r : g_trace) {
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, g_trace[0].ev, r.ev);
+		fprintf(stderr, "[cvb200 trace]   slot %d %-14s %8.3f ms\n", r.slot, r.tag, ms);
+	}
+	for (auto& r : g_trace) cudaEventDestroy(r.ev);
+	g_trace.clear();
+}
+
 } // namespace cvb
 
 using namespace cvb;
@@ -73,6 +104,9 @@ extern "C" {
 int cvb200_init(int device)
 {
 	CVB_REQUIRE(device >= 0, CVB200_E_INVALID_PARAMETER);
+	// the pipelined entry points keep up to a dozen streams busy: ask for enough hardware work queues (only effective when this is the process's first CUDA call;
+	// an application that initialises CUDA itself sets CUDA_DEVICE_MAX_CONNECTIONS=32 in its environment)
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 	int count = 0;
 	CVB_CUDA(cudaGetDeviceCount(&count));
 	CVB_REQUIRE(device < count, CVB200_E_INVALID_PARAMETER);
