@@ -119,7 +119,7 @@ struct KhtWalker {
 		M = kw_rotr(load_row(base, ro), 24);
 		B = load_row(base, ro + WW);
 		Fd = load_row(base, ro + 2 * WW);
-		pend = 0; plo = 0; phi = 0;
+		pend = 0; // plo / phi are deliberately left alone: writing them here would have to wait for a far-row load that may still be in flight
 		c = 30 - ip;
 	}
 	// Erase the current pixel (window + memory), then Algorithm 6: move to the first remaining neighbour in the order TL, T, TR, L, R, BL, B, BR.
@@ -162,6 +162,7 @@ KW_FN unsigned int kht_link_string(unsigned int* base, int WW, unsigned int seed
 {
 	int n = 0; // a signed 32-bit index: one IMAD.WIDE per address
 	KhtWalker wk;
+	wk.plo = 0; wk.phi = 0;
 	wk.xy = seedXY;
 	wk.centre(base, WW, 12); // a seed is the raster-first pixel left: nothing above it or to its left, the walk starts rightwards or downwards
 	do {

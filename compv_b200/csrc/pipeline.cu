@@ -111,10 +111,11 @@ int run_pipeline(Job& j, cudaStream_t callerStream)
 	// Sub-batches.  The linking kernel's duration hardly depends on how many frames it holds, and a slot's chain is Canny -> linking -> voting/peaks:
 	//   * device frames: as many sub-batches as slots, all enqueued at once (a slot that has to be waited for and refilled leaves the GPU idle for one linking latency);
 	//   * host frames: the upload paces everything, so a ring of smaller sub-batches keeps the tail (the last sub-batch's chain after its upload) short.
-	const size_t nSlotsWanted = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SLOTS", 6)));
+	// host frames: 256 frames take ~10 ms to upload and ~30 ms to flow through a slot while the GPU is busy with the others -> 8 slots keep the copy engine fed
+	const size_t nSlotsWanted = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SLOTS", j.onHost ? 8 : 6)));
 	size_t sub;
 	if (j.batch <= 8) sub = j.batch; // a handful of frames: one sub-batch, no ring
-	else if (j.onHost) { sub = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SUB", 128))); if (sub * 3 > j.batch) sub = std::max<size_t>(1, div_up(j.batch, 3)); }
+	else if (j.onHost) { sub = static_cast<size_t>(std::max(1, env_int("CVB200_PIPE_SUB", 256))); if (sub * 3 > j.batch) sub = std::max<size_t>(1, div_up(j.batch, 3)); }
 	else { const int forced = env_int("CVB200_PIPE_SUB", 0); sub = forced > 0 ? static_cast<size_t>(forced) : std::max<size_t>(div_up(j.batch, nSlotsWanted), std::min<size_t>(j.batch, 16)); }
 	j.sub = sub;
 	const size_t nSub = div_up(j.batch, sub);
@@ -122,7 +123,14 @@ int run_pipeline(Job& j, cudaStream_t callerStream)
 	while (st.slots.size() < nSlots) {
 		PipeSlot* s = new (std::nothrow) PipeSlot();
 		CVB_REQUIRE(s, CVB200_E_OUT_OF_MEMORY);
-		CVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		// Earlier slots get the higher priority: the Canny kernels of all slots are queued at once and would otherwise share the SMs evenly and all finish
+		// together; with priorities slot 0's Canny finishes first and its linking kernel (a long latency chain) starts while the later slots are still in Canny.
+		int prLo = 0, prHi = 0;
+		CVB_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi)); // numerically lower = higher priority
+		int pr = prHi + static_cast<int>(st.slots.size());
+		if (pr > prLo) pr = prLo;
+		if (env_int("CVB200_PIPE_PRIORITIES", 1) == 0) pr = prLo;
+		CVB_CUDA(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, pr));
 		CVB_CUDA(cudaEventCreateWithFlags(&s->evIn, cudaEventDisableTiming));
 		s->hough.lastGs = 1.0;
 		st.slots.push_back(s);
