@@ -317,6 +317,35 @@ def ccl_lsl(which, img, width=None, threads=1, iters=0):
     return out
 
 
+def ccl_lsl_extract_ref(img, blob=True, width=None, threads=1):
+    """The REFERENCE's CompVConnectedComponentLabelingResultLSL::extract (ccl_lsl_result.cxx:100-134): list of (n, 2) int16 arrays (x, y), one per label;
+    for segments also the boxes the reference derives from them (ccl_lsl_result.cxx:187-230)."""
+    r = ref(threads)
+    w, h, stride = _frame_args(img, width)
+    nl, npnt = C.c_size_t(0), C.c_size_t(0)
+    _chk(r.ref_ccl_lsl_extract(_p(img), _sz(w), _sz(h), _sz(stride), int(bool(blob)), None, _sz(0), None, _sz(0), C.byref(nl), C.byref(npnt), None), "ref_ccl_lsl_extract")
+    counts = np.zeros(max(nl.value, 1), np.int32)
+    pts = np.zeros((max(npnt.value, 1), 2), np.int16)
+    boxes = np.zeros((max(nl.value, 1), 4), np.int16)
+    _chk(r.ref_ccl_lsl_extract(_p(img), _sz(w), _sz(h), _sz(stride), int(bool(blob)), _p(counts), _sz(len(counts)), _p(pts), _sz(len(pts)), C.byref(nl), C.byref(npnt),
+                               None if blob else _p(boxes)), "ref_ccl_lsl_extract")
+    out, o = [], 0
+    for a in range(nl.value):
+        out.append(pts[o:o + counts[a]].copy())
+        o += counts[a]
+    return out, (None if blob else boxes[:nl.value])
+
+
+def hough_to_cartesian_ref(kht, width, height, rho, theta):
+    """The REFERENCE's CompVHough::toCartesian (houghkht.cxx:1249-1280 / houghsht.cxx:566-592): (n, 4) float32 {a.x, a.y, b.x, b.y}."""
+    r = ref(1)
+    rho = np.ascontiguousarray(rho, np.float32)
+    theta = np.ascontiguousarray(theta, np.float32)
+    out = np.zeros((len(rho), 4), np.float32)
+    _chk(r.ref_hough_to_cartesian(int(bool(kht)), _sz(width), _sz(height), _sz(len(rho)), _p(rho), _p(theta), _p(out)), "ref_hough_to_cartesian")
+    return out
+
+
 def ccl_lmser(which, img, delta=2, min_area=0.0055 * 0.0055, max_area=0.8 * 0.15, max_variation=0.3, min_diversity=0.2, connectivity=8, width=None, threads=1, iters=0,
               point_cap=None):
     """Linear-time MSER.  Defaults are the reference's unit-test parameters (unittests/ccl_mser.cxx:26-46).

@@ -444,6 +444,52 @@ int ref_ccl_lsl(const uint8_t* img, size_t w, size_t h, size_t stride, int32_t* 
 	return 0;
 }
 
+// ---- section 8f-4: the consumers of the PLSL / Hough results ----
+// CompVConnectedComponentLabelingResultLSL::extract (core/ccl/compv_core_ccl_lsl_result.cxx:100-134, 308-416): counts[label] points per label, points (x, y) concatenated in label order.
+// type: 0 = COMPV_CCL_EXTRACT_TYPE_SEGMENT, 1 = COMPV_CCL_EXTRACT_TYPE_BLOB.  Also the boxes computed FROM the extracted segments (ccl_lsl_result.cxx:187-230) when boxesFromSegments != NULL.
+int ref_ccl_lsl_extract(const uint8_t* img, size_t w, size_t h, size_t stride, int type, int32_t* counts, size_t countCap, int16_t* points, size_t pointCap, size_t* nLabels, size_t* nPoints,
+	int16_t* boxesFromSegments)
+{
+	CompVMatPtr image;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVConnectedComponentLabelingPtr ccl;
+	SHIM_CHECK(CompVConnectedComponentLabeling::newObj(&ccl, COMPV_PLSL_ID));
+	CompVConnectedComponentLabelingResultPtr result;
+	SHIM_CHECK(ccl->process(image, &result));
+	const CompVConnectedComponentLabelingResultLSL* lsl = CompVConnectedComponentLabeling::reinterpret_castr<CompVConnectedComponentLabelingResultLSL>(result);
+	if (!lsl) return -2;
+	CompVConnectedComponentPointsVector pts;
+	SHIM_CHECK(lsl->extract(pts, type ? COMPV_CCL_EXTRACT_TYPE_BLOB : COMPV_CCL_EXTRACT_TYPE_SEGMENT));
+	size_t np = 0;
+	for (size_t a = 0; a < pts.size(); ++a) {
+		if (counts && a < countCap) counts[a] = static_cast<int32_t>(pts[a].size());
+		for (size_t k = 0; k < pts[a].size(); ++k, ++np) if (points && np < pointCap) { points[2 * np] = pts[a][k].x; points[2 * np + 1] = pts[a][k].y; }
+	}
+	if (nLabels) *nLabels = pts.size();
+	if (nPoints) *nPoints = np;
+	if (boxesFromSegments && !type) {
+		CompVConnectedComponentBoundingBoxesVector bb;
+		SHIM_CHECK(lsl->boundingBoxes(pts, bb));
+		memcpy(boxesFromSegments, bb.data(), (bb.size() < countCap ? bb.size() : countCap) * sizeof(CompVConnectedComponentBoundingBox));
+	}
+	return 0;
+}
+
+// CompVHough::toCartesian (houghkht.cxx:1249-1280, houghsht.cxx:566-592): out = n x {a.x, a.y, b.x, b.y}
+int ref_hough_to_cartesian(int kht, size_t w, size_t h, size_t n, const float* rho, const float* theta, float* out)
+{
+	CompVHoughPtr hough;
+	SHIM_CHECK(CompVHough::newObj(&hough, kht ? COMPV_HOUGHKHT_ID : COMPV_HOUGHSHT_ID, 1.f, 1.f, 1));
+	CompVHoughLineVector polar(n);
+	for (size_t i = 0; i < n; ++i) { polar[i].rho = rho[i]; polar[i].theta = theta[i]; polar[i].strength = 1; }
+	CompVLineFloat32Vector cart;
+	SHIM_CHECK(hough->toCartesian(w, h, polar, cart));
+	if (cart.size() != n) return -2;
+	for (size_t i = 0; i < n; ++i) { out[4 * i] = cart[i].a.x; out[4 * i + 1] = cart[i].a.y; out[4 * i + 2] = cart[i].b.x; out[4 * i + 3] = cart[i].b.y; }
+	return 0;
+}
+
 // ---- a12: CompVConnectedComponentLabeling (COMPV_LMSER_ID) ----
 // regions are returned in the reference's order: regionSizes[i] = number of points, regionBoxes[4*i..] = {left, top, right, bottom},
 // points (int16 x, y pairs) concatenated in region order up to pointCap points. *regionCount / *pointCount receive the totals.

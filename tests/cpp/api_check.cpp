@@ -92,6 +92,15 @@ static COMPV_ERROR_CODE run(size_t width, size_t height, const char* framePath, 
 		}
 		COMPV_CHECK_EXP_RETURN(!dump(out + "/plsl_blobs.i32", flat.data(), flat.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
 	}
+	for (int t = 0; t < 2; ++t) { // every label: count, then (x, y) pairs
+		const CompVConnectedComponentPointsVector& v = t ? segs : blobs;
+		std::vector<int32_t> flat;
+		for (size_t a = 0; a < v.size(); ++a) {
+			flat.push_back(static_cast<int32_t>(v[a].size()));
+			for (size_t k = 0; k < v[a].size(); ++k) { flat.push_back(v[a][k].x); flat.push_back(v[a][k].y); }
+		}
+		COMPV_CHECK_EXP_RETURN(!dump(out + (t ? "/plsl_all_segments.i32" : "/plsl_all_blobs.i32"), flat.data(), flat.size()), COMPV_ERROR_CODE_E_INVALID_STATE);
+	}
 	// the text pipeline's clean-up step (samples/text_recognition/main.cxx:93-104)
 	CompVMatPtr strel, closed;
 	COMPV_CHECK_CODE_RETURN(CompVMathMorph::buildStructuringElement(&strel, CompVSizeSz(3, 3), COMPV_MATH_MORPH_STREL_TYPE_RECT));

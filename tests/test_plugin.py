@@ -30,6 +30,7 @@ def test_plugin_without_a_gpu_registers_nothing():
     assert out["gpu_launches"] == 0
     # the reference's own CPU implementations still answer (x86 build: Sobel shows the SSE4.1 max quirk)
     assert out["canny_equal"] and out["kht_equal"] and out["sht_equal"] and out["fast_equal"] and out["sobel_equal_x86_quirk"]
+    assert out["hog_close"] and out["plsl_equal"] and out["plsl_extract_equal"] and out["plsl_segment_boxes_ok"] and out["mser_equal"]
 
 
 @pytest.mark.gpu
@@ -40,3 +41,6 @@ def test_plugin_routes_the_reference_api_to_the_gpu():
     assert out["gpu_launches"] > 0                          # the reference's factory handed out the B200 objects
     assert out["canny_equal"] and out["kht_equal"] and out["sht_equal"] and out["fast_equal"]
     assert out["sobel_equal"]                               # true frame maximum: the B200 default, not the x86 SSE4.1 lane quirk
+    # COMPV_HOGS_ID through CompVHOG::newObj, COMPV_PLSL_ID / COMPV_LMSER_ID through CompVConnectedComponentLabeling::newObj (+ the result classes' accessors)
+    assert out["hog_size_equal"] and out["hog_bit_exact_vs_oracle"]
+    assert out["plsl_equal"] and out["plsl_extract_equal"] and out["plsl_segment_boxes_ok"] and out["mser_equal"]
