@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
-from frames import frame_g, frame_text
+from frames import frame_g, frame_text, frame_smooth
 
 W, H = 3840, 2160
 
@@ -103,13 +103,13 @@ def test_cuda_lmser_4k_multi_pass(cvb):
     import torch
     from compv_b200 import _ffi
     kw = dict(delta=2, min_area=0.0055 * 0.0055, max_area=0.8 * 0.15, max_variation=0.3, min_diversity=0.2, connectivity=8)
-    frames = np.stack([frame_g(W, H, 31), frame_text(W, H, 8), frame_g(W, H, 32), frame_text(W, H, 9)])
+    frames = np.stack([frame_g(W, H, 31), frame_smooth(W, H, 8), frame_g(W, H, 32), frame_smooth(W, H, 9)])
     ccl = cvb.CompVConnectedComponentLabeling.newObj(_ffi.LMSER_ID, **kw)
     d_in = torch.from_numpy(frames).cuda()
     na, results = ccl.process_dev(d_in, W, H, W, batch=4, want_results=True, stream=torch.cuda.current_stream().cuda_stream)
     for k in range(4):
         want = oracle.ccl_lmser("orc", frames[k], **kw)
-        assert na[k] == len(want["sizes"]) and (k % 2 == 1 or na[k] > 0)
+        assert na[k] == len(want["sizes"]) > 0
         assert _mser_canonical(results[k].regions()) == _mser_canonical(want)
     one = ccl.process(frames[1])                                    # host entry point, single frame
     assert _mser_canonical(one.regions()) == _mser_canonical(oracle.ccl_lmser("orc", frames[1], **kw))
@@ -122,7 +122,7 @@ def test_cuda_lmser_1080p_batch_over_one_pass(cvb):
     from compv_b200 import _ffi
     w, h, batch = 1920, 1080, 17
     kw = dict(delta=2, min_area=0.0055 * 0.0055, max_area=0.8 * 0.15, max_variation=0.3, min_diversity=0.2, connectivity=8)
-    distinct = [frame_g(w, h, 40), frame_text(w, h, 11), frame_g(w, h, 41)]
+    distinct = [frame_g(w, h, 40), frame_smooth(w, h, 11), frame_g(w, h, 41)]
     frames = np.stack([distinct[k % 3] for k in range(batch)])
     want = [oracle.ccl_lmser("orc", f, **kw) for f in distinct]
     ccl = cvb.CompVConnectedComponentLabeling.newObj(_ffi.LMSER_ID, **kw)
