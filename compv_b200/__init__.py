@@ -396,6 +396,24 @@ def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
     return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]
 
 
+def init_devices(count=0):
+    """cvb200_init_devices: every device of the process (count <= 0) or the first `count`; returns how many are active."""
+    check(lib().cvb200_init_devices(int(count)), "cvb200_init_devices")
+    return int(lib().cvb200_active_device_count())
+
+
+def canny_kht_process_batch_multi(canny, hough, images, width=None, capacity=4096):
+    """Host frames spread over every initialised device in-process; cvb200_canny_kht_process_batch_multi."""
+    assert images.ndim == 3 and images.flags.c_contiguous
+    b, h, stride = images.shape
+    w = stride if width is None else int(width)
+    lines = np.zeros((b, capacity), LINE_DTYPE)
+    counts = np.zeros(b, np.uint64)
+    check(lib().cvb200_canny_kht_process_batch_multi(canny._h, hough._h, vp(images), sz(w), sz(h), sz(stride), sz(b), sz(h * stride), vp(lines), sz(capacity), vp(counts)),
+          "cvb200_canny_kht_process_batch_multi")
+    return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]
+
+
 def canny_kht_process_batch_dev(canny, hough, d_images, width, height, stride, batch, capacity=4096, frame_pitch=0, stream=0):
     """Device frames -> list of per-frame line arrays (host); cvb200_canny_kht_process_batch_dev."""
     lines = np.zeros((batch, capacity), LINE_DTYPE)

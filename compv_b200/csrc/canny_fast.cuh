@@ -292,11 +292,8 @@ static int launch_canny_fast_t(const FastParams& p0, size_t batch, cudaStream_t 
 	p.useTma = make_u8_tile_map(&map, p.in, p.W, p.H, p.stride, p.framePitch, batch, CF_INW * 4, G::IN_ROWS) ? 1 : 0;
 	p.vecStore = (((reinterpret_cast<uintptr_t>(p.cls) | p.stride | p.framePitch) & 3) == 0) ? 1 : 0;
 	auto kern = canny_front_fast_kernel<BKS>;
-	static bool attrSet = false;
-	if (!attrSet) {
-		CVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)));
-		attrSet = true;
-	}
+	static std::atomic<unsigned int> attrSet{0};
+	CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(kern), static_cast<int>(G::SMEM), attrSet));
 	dim3 grid(static_cast<unsigned>(div_up(p.W, CF_TW)), static_cast<unsigned>(div_up(p.H, CF_TH)), static_cast<unsigned>(batch));
 	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 	{
@@ -424,12 +421,9 @@ static int launch_sobel_fast(const FastParams& p0, unsigned int* gmax, int gmaxL
 	memset(&map, 0, sizeof(map));
 	p.useTma = make_u8_tile_map(&map, p.in, p.W, p.H, p.stride, p.framePitch, batch, CF_INW * 4, G::IN_ROWS) ? 1 : 0;
 	p.vecStore = (((reinterpret_cast<uintptr_t>(p.cls) | p.stride | p.framePitch) & 3) == 0) ? 1 : 0;
-	static bool attrSet = false;
-	if (!attrSet) {
-		CVB_CUDA(cudaFuncSetAttribute(sobel_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)));
-		CVB_CUDA(cudaFuncSetAttribute(sobel_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)));
-		attrSet = true;
-	}
+	static std::atomic<unsigned int> attrSet2{0}, attrSet3{0};
+	CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(sobel_fast_kernel<2>), static_cast<int>(G::SMEM), attrSet2));
+	CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(sobel_fast_kernel<3>), static_cast<int>(G::SMEM), attrSet3));
 	dim3 grid(static_cast<unsigned>(div_up(p.W, CF_TW)), static_cast<unsigned>(div_up(p.H, CF_TH)), static_cast<unsigned>(batch));
 	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 	{ KernelScope ks_("edge_gmax", stream);

@@ -15,13 +15,21 @@ namespace cvb {
 // ---- runtime state (runtime.cu) ----
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_device;          // -1 when not initialised
+extern std::atomic<int> g_device_count;    // devices initialised by cvb200_init_devices (1 after cvb200_init)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int num_sms();
 
 #define CVB_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return ::cvb::cuda_fail(e__, #x, __FILE__, __LINE__); } while (0)
 #define CVB_CHECK(x) do { int c__ = (x); if (c__ != CVB200_S_OK) return c__; } while (0)
 #define CVB_REQUIRE(cond, code) do { if (!(cond)) return (code); } while (0)
-#define CVB_REQUIRE_INIT() do { if (::cvb::g_device.load() < 0) return CVB200_E_NOT_INITIALIZED; } while (0)
+// Every entry point runs on the device its THREAD is bound to: the one given to cvb200_init (any thread of the application), or the one a multi-device worker
+// thread was started for (pipeline.cu).  cudaSetDevice is per thread, so it is (re)applied here whenever the calling thread is not on that device yet.
+int ensure_device();
+int bound_device();
+void bind_thread_to_device(int device);  // multi-device workers
+#define CVB_REQUIRE_INIT() do { if (::cvb::g_device.load() < 0) return CVB200_E_NOT_INITIALIZED; CVB_CHECK(::cvb::ensure_device()); } while (0)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and kernel: `flags` is a per-call-site bit set indexed by device
+int set_max_smem_once(const void* func, int bytes, std::atomic<unsigned int>& flags);
 // call after every kernel launch: counts it and surfaces launch-configuration errors immediately
 #define CVB_LAUNCHED() do { ::cvb::g_launches.fetch_add(1, std::memory_order_relaxed); CVB_CUDA(cudaGetLastError()); } while (0)
 

@@ -331,8 +331,8 @@ static int fast_launch(cvb200_corner_dete* d, const uint8_t* image, size_t width
 	alignas(64) CUtensorMap map;
 	memset(&map, 0, sizeof(map));
 	p.useTma = make_u8_tile_map(&map, image, width, height, stride, framePitch, batch, FA_INW * 4, FA_IN_ROWS) ? 1 : 0;
-	static bool attrSet = false;
-	if (!attrSet) { CVB_CUDA(cudaFuncSetAttribute(fast_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(FA_SMEM))); attrSet = true; }
+	static std::atomic<unsigned int> attrSet{0};
+	CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(fast_detect_kernel), static_cast<int>(FA_SMEM), attrSet));
 	dim3 grid(static_cast<unsigned>(div_up(width, FA_TW)), static_cast<unsigned>(div_up(height, FA_TH)), static_cast<unsigned>(batch));
 	CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 	{

@@ -889,11 +889,9 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	  kht_peaks_emit_kernel<<<dim3(g.nTheta, B), 256, 0, stream>>>(h->acc.as<int>(), h->rowCount.as<unsigned int>(), h->votes.as<KhtVote>(), dFrames, dMeta, g); }
 	CVB_LAUNCHED();
 	{
-		static std::once_flag once;
-		static cudaError_t attrErr = cudaSuccess;
+		static std::atomic<unsigned int> attrSet{0};
 		const int smem = KSORT_SMEM_ITEMS * (8 + 4 + 4);
-		std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kht_peaks_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
-		CVB_CUDA(attrErr);
+		CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(kht_peaks_sort_kernel), smem, attrSet));
 		const unsigned int lim = (h->maxLines <= 0) ? static_cast<unsigned int>(INT_MAX) : static_cast<unsigned int>(h->maxLines);
 		KernelScope ks_("kht_peaks_sort", stream);
 		kht_peaks_sort_kernel<<<B, KSORT_THREADS, smem, stream>>>(h->votes.as<KhtVote>(), h->sortItems.as<sse_item>(), h->sortLists.as<unsigned int>(), h->sortRanges.as<int>(), h->acc.as<int>(),

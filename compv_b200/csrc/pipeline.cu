@@ -9,7 +9,10 @@
 #include "hough.cuh"
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdlib>
+#include <functional>
+#include <thread>
 #include <vector>
 
 using namespace cvb;
@@ -158,9 +161,93 @@ int run_pipeline(Job& j, cudaStream_t callerStream)
 	return rc;
 }
 
+// ---- several devices in one process: one persistent worker thread per device, bound to it for life (cudaSetDevice is per thread) with its own ring of slots
+// (the thread_local PipeState above).  Frames are independent, so a batch is cut into contiguous shards, one per device, with no exchange between them.
+struct DeviceWorker {
+	int device = 0;
+	std::thread th;
+	std::mutex m;
+	std::condition_variable cv;
+	std::function<int()> job;
+	bool hasJob = false, done = false, stop = false;
+	int rc = CVB200_S_OK;
+	void loop() {
+		bind_thread_to_device(device);
+		for (;;) {
+			std::function<int()> f;
+			{
+				std::unique_lock<std::mutex> lk(m);
+				cv.wait(lk, [&] { return stop || hasJob; });
+				if (stop) return;
+				f = job; hasJob = false;
+			}
+			int r = ensure_device();
+			if (r == CVB200_S_OK) r = f();
+			{ std::lock_guard<std::mutex> lk(m); rc = r; done = true; }
+			cv.notify_all();
+		}
+	}
+	void submit(const std::function<int()>& f) { { std::lock_guard<std::mutex> lk(m); job = f; hasJob = true; done = false; } cv.notify_all(); }
+	int wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return done; }); return rc; }
+};
+struct DevicePool {
+	std::vector<DeviceWorker*> workers;
+	std::mutex m;
+	~DevicePool() { for (DeviceWorker* w : workers) { { std::lock_guard<std::mutex> lk(w->m); w->stop = true; } w->cv.notify_all(); if (w->th.joinable()) w->th.join(); delete w; } }
+	DeviceWorker* get(int device) {
+		std::lock_guard<std::mutex> lk(m);
+		while (static_cast<int>(workers.size()) <= device) {
+			DeviceWorker* w = new DeviceWorker();
+			w->device = static_cast<int>(workers.size());
+			w->th = std::thread([w] { w->loop(); });
+			workers.push_back(w);
+		}
+		return workers[device];
+	}
+};
+DevicePool& device_pool() { static DevicePool p; return p; }
+
 } // namespace
 
 extern "C" {
+
+int cvb200_canny_kht_process_batch_multi(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride,
+	size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(canny && hough && images && counts && width && height && stride >= width && (lines || !capacity), CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(canny->id == CVB200_CANNY_ID && hough->id == CVB200_HOUGHKHT_ID, CVB200_E_INVALID_PARAMETER);
+	if (!batch) return CVB200_S_OK;
+	if (!framePitch) framePitch = stride * height;
+	CVB_REQUIRE(framePitch >= stride * height, CVB200_E_INVALID_PARAMETER);
+	const size_t nDev = std::min<size_t>(static_cast<size_t>(std::max(1, g_device_count.load())), batch);
+	std::lock_guard<std::mutex> l1(canny->mutex);
+	std::lock_guard<std::mutex> l2(hough->mutex);
+	std::vector<Job> jobs(nDev);
+	std::vector<cvb200_hough> houghCopies(nDev); // each shard reports its own lastGs; the caller's object gets the last shard's
+	std::vector<cvb200_edge_dete> cannyCopies(nDev);
+	const size_t per = div_up(batch, nDev);
+	size_t used = 0;
+	for (size_t d = 0; d < nDev; ++d) {
+		const size_t f0 = d * per;
+		if (f0 >= batch) break;
+		const size_t nf = std::min(per, batch - f0);
+		copy_params(houghCopies[d], *hough);
+		houghCopies[d].lastGs = 1.0;
+		copy_params(cannyCopies[d], *canny);
+		jobs[d] = Job{ &cannyCopies[d], &houghCopies[d], images + f0 * framePitch, true, width, height, stride, nf, framePitch, lines ? lines + f0 * capacity : nullptr, capacity, counts + f0, 0, 0 };
+		Job* jp = &jobs[d];
+		device_pool().get(static_cast<int>(d))->submit([jp] { return run_pipeline(*jp, nullptr); });
+		++used;
+	}
+	int rc = CVB200_S_OK;
+	for (size_t d = 0; d < used; ++d) { const int r = device_pool().get(static_cast<int>(d))->wait(); if (rc == CVB200_S_OK) rc = r; }
+	if (rc == CVB200_S_OK) {
+		hough->lastGs = houghCopies[used - 1].lastGs;
+		for (size_t d = 0; d < used; ++d) if (canny->hystRounds < cannyCopies[d].hystRounds) canny->hystRounds = cannyCopies[d].hystRounds;
+	}
+	return rc;
+}
 
 int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride,
 	size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts)

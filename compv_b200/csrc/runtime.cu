@@ -17,6 +17,7 @@ namespace cvb {
 
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_device{-1};
+std::atomic<int> g_device_count{0};
 static int g_num_sms = 0;
 static thread_local std::string t_last_cuda_error;
 
@@ -30,6 +31,31 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 }
 
 int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+
+static thread_local int t_wanted_device = -1; // >= 0: this thread is a multi-device worker
+static thread_local int t_bound_device = -1;  // what cudaSetDevice was last called with on this thread
+int bound_device() { return t_wanted_device >= 0 ? t_wanted_device : g_device.load(); }
+void bind_thread_to_device(int device) { t_wanted_device = device; }
+int ensure_device()
+{
+	const int want = bound_device();
+	if (want != t_bound_device) {
+		CVB_CUDA(cudaSetDevice(want));
+		t_bound_device = want;
+	}
+	return CVB200_S_OK;
+}
+int set_max_smem_once(const void* func, int bytes, std::atomic<unsigned int>& flags)
+{
+	static std::mutex m;
+	const unsigned int bit = 1u << (bound_device() & 31);
+	if (flags.load(std::memory_order_acquire) & bit) return CVB200_S_OK;
+	std::lock_guard<std::mutex> lock(m);
+	if (flags.load(std::memory_order_relaxed) & bit) return CVB200_S_OK;
+	CVB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	flags.fetch_or(bit, std::memory_order_release);
+	return CVB200_S_OK;
+}
 
 // ---- per-kernel timing ----
 std::atomic<int> g_profiling{0};
@@ -124,12 +150,32 @@ int cvb200_init(int device)
 	g_num_sms = prop.multiProcessorCount;
 	CVB_CUDA(cudaFree(0)); // force primary-context creation
 	g_device.store(device);
+	if (g_device_count.load() < 1) g_device_count.store(1);
 	return CVB200_S_OK;
 }
+
+// cvb200_init(int device_count).  Initialises devices 0 .. count-1 (count <= 0: every device of the process) for the *_multi batch entry points, which
+// spread the frames of a batch over them (one worker thread + its own streams and scratch per device); every other entry point keeps running on device 0.
+int cvb200_init_devices(int device_count)
+{
+	int count = 0;
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+	CVB_CUDA(cudaGetDeviceCount(&count));
+	CVB_REQUIRE(count > 0, CVB200_E_CUDA);
+	if (device_count <= 0 || device_count > count) device_count = count;
+	for (int d = device_count - 1; d >= 0; --d) { // device 0 last: it stays the calling thread's current device
+		CVB_CHECK(cvb200_init(d));
+	}
+	g_device_count.store(device_count);
+	return CVB200_S_OK;
+}
+
+int cvb200_active_device_count(void) { return g_device.load() >= 0 ? g_device_count.load() : 0; }
 
 int cvb200_deinit(void)
 {
 	g_device.store(-1);
+	g_device_count.store(0);
 	return CVB200_S_OK;
 }
 

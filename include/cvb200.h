@@ -119,6 +119,10 @@ typedef void* cvb200_stream_t; /* cudaStream_t */
  * ============================================================================================== */
 /* Binds the calling process to CUDA device `device` (>=0). Must be called before anything else. Idempotent. */
 CVB200_API int cvb200_init(int device);
+/* SURVEY 8(b) `cvb200_init(int device_count)`: initialises devices 0 .. device_count-1 (<= 0: every device of the process) for the *_multi batch entry points, which
+ * spread the frames of a batch over them in-process (one worker thread, its streams and scratch per device; no torchrun needed). Device 0 serves every other entry point. */
+CVB200_API int cvb200_init_devices(int device_count);
+CVB200_API int cvb200_active_device_count(void);
 CVB200_API int cvb200_deinit(void);
 /* 1 when cvb200_init succeeded (reference: CompVGpu::isActiveAndEnabled, gpu/include/compv/gpu/compv_gpu.h:31-33) */
 CVB200_API int cvb200_is_active(void);
@@ -366,6 +370,9 @@ CVB200_API int cvb200_morph_process_dev(const uint8_t* in, size_t width, size_t 
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
 CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);
+/* The same call spread over every device initialised by cvb200_init_devices: frames are independent, the batch is cut into one contiguous shard per device and each
+ * shard runs the pipeline above on its device from its own host thread (no collective). Results land in the caller's arrays exactly as with one device. */
+CVB200_API int cvb200_canny_kht_process_batch_multi(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);
 /* Same pipeline on frames that are already in device memory (`images` is a device pointer; `lines` / `counts` are host arrays). The work is ordered after what was
  * queued on `stream` before the call; the call returns when the lines are in host memory. Sub-batches of the frames run on several internal streams so that the
  * linking stage of one sub-batch overlaps the other stages of its neighbours (environment: CVB200_PIPE_SUB frames per sub-batch, CVB200_PIPE_SLOTS in flight). */

@@ -234,3 +234,25 @@ def test_cuda_canny_hysteresis_needs_many_rounds(cvb):
     want = oracle.edge_dete("orc", img, "canny", 30.0, 400.0, 3)
     assert np.array_equal(got, want)
     assert (want == 255).sum() > 2000       # the closure really travelled
+
+
+@pytest.mark.gpu
+def test_cuda_canny_kht_multi_device_in_process(cvb):
+    """cvb200_init_devices + cvb200_canny_kht_process_batch_multi: the batch is cut into one shard per device, each shard runs on its device from a worker thread
+    of THIS process (no torchrun).  With one GPU on the box this is one shard through the same worker path; with more (gpurun --gpus N) every device takes part."""
+    from compv_b200 import _ffi
+    n = cvb.init_devices(0)
+    assert n >= 1
+    w, h, batch = 320, 200, 4 * n + 3
+    frames = np.stack([frame_g(w, h, 1200 + k) if k % 2 else frame_smooth(w, h, 50 + k) for k in range(batch)])
+    canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
+    canny.set_preblur(5, 1.0)
+    kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 30)
+    for _ in range(2):
+        got = cvb.canny_kht_process_batch_multi(canny, kht, frames, width=w)
+        for k in range(batch):
+            want, gs = oracle.hough_kht("orc", canny_edges(frames[k]), 1.0, 1.0, 30)
+            same_lines(got[k], want)
+        assert kht.getFloat64(_ffi.HOUGHKHT_GET_FLT64_GS) == gs
+    # the single-device entry points still work afterwards (device 0)
+    same_lines(kht.process(canny_edges(frames[0])), oracle.hough_kht("orc", canny_edges(frames[0]), 1.0, 1.0, 30)[0])
