@@ -396,6 +396,25 @@ def canny_kht_process_batch(canny, hough, images, width=None, capacity=4096):
     return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]
 
 
+def image_to_grayscale(pixel_format, data, width, height, stride):
+    """cvb200_image_to_grayscale: host frame bytes in `pixel_format` (COMPV_SUBTYPE_PIXELS_* value) -> (height, stride) gray plane."""
+    data = np.ascontiguousarray(data, np.uint8)
+    out = np.zeros((height, stride), np.uint8)
+    check(lib().cvb200_image_to_grayscale(int(pixel_format), vp(data), sz(width), sz(height), sz(stride), vp(out)), "cvb200_image_to_grayscale")
+    return out
+
+
+def canny_kht_process_batch_fmt(canny, hough, pixel_format, frames, width, height, stride, frame_pitch_bytes, capacity=4096):
+    """Host frames in a camera format (batch, frame_pitch_bytes) uint8 -> list of per-frame line arrays; cvb200_canny_kht_process_batch_fmt."""
+    assert frames.ndim == 2 and frames.flags.c_contiguous and frames.shape[1] == frame_pitch_bytes
+    b = frames.shape[0]
+    lines = np.zeros((b, capacity), LINE_DTYPE)
+    counts = np.zeros(b, np.uint64)
+    check(lib().cvb200_canny_kht_process_batch_fmt(canny._h, hough._h, int(pixel_format), vp(frames), sz(width), sz(height), sz(stride), sz(b), sz(frame_pitch_bytes), vp(lines), sz(capacity),
+                                                   vp(counts)), "cvb200_canny_kht_process_batch_fmt")
+    return [lines[f, :min(int(counts[f]), capacity)].copy() for f in range(b)]
+
+
 def init_devices(count=0):
     """cvb200_init_devices: every device of the process (count <= 0) or the first `count`; returns how many are active."""
     check(lib().cvb200_init_devices(int(count)), "cvb200_init_devices")

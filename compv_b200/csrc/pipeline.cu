@@ -24,7 +24,7 @@ struct PipeSlot {
 	cudaEvent_t evIn = nullptr;       // this slot's upload has landed
 	cvb200_edge_dete canny;
 	cvb200_hough hough;
-	DevBuf in, edges;
+	DevBuf in, edges, raw;
 	size_t f0 = 0, nf = 0;            // frames in flight
 	bool busy = false;
 	const uint8_t* dIn = nullptr;     // where the sub-batch's frames are on the device
@@ -58,6 +58,7 @@ struct Job {
 	size_t width, height, stride, batch, framePitch;
 	cvb200_hough_line_t* lines; size_t capacity; size_t* counts;
 	size_t frameBytes, sub;
+	int pixelFormat = 0; size_t bpp = 1; // host frames in a camera format: uploaded as they are (luma-carrying plane only), made gray on the device (gray.cu)
 };
 
 int slot_enqueue(PipeState& st, PipeSlot& s, const Job& j, size_t f0, size_t nf)
@@ -66,9 +67,20 @@ int slot_enqueue(PipeState& st, PipeSlot& s, const Job& j, size_t f0, size_t nf)
 	if (j.onHost) {
 		CVB_CHECK(s.in.ensure(j.sub * j.frameBytes));
 		// uploads go through one copy stream in order; the copy may start as soon as this slot's previous kernels are done (finish() has synchronised them)
-		CVB_CUDA(cudaMemcpy2DAsync(s.in.p, j.frameBytes, j.images + f0 * j.framePitch, j.framePitch, j.frameBytes, nf, cudaMemcpyHostToDevice, st.sCopy));
-		CVB_CUDA(cudaEventRecord(s.evIn, st.sCopy));
-		CVB_CUDA(cudaStreamWaitEvent(s.stream, s.evIn, 0));
+		if (j.bpp == 1) { // gray, or a planar / semi-planar YUV format: the Y plane is the gray image, the chroma planes never cross PCIe
+			CVB_CUDA(cudaMemcpy2DAsync(s.in.p, j.frameBytes, j.images + f0 * j.framePitch, j.framePitch, j.frameBytes, nf, cudaMemcpyHostToDevice, st.sCopy));
+			CVB_CUDA(cudaEventRecord(s.evIn, st.sCopy));
+			CVB_CUDA(cudaStreamWaitEvent(s.stream, s.evIn, 0));
+		}
+		else {
+			const size_t rawBytes = j.frameBytes * j.bpp;
+			CVB_CHECK(s.raw.ensure(j.sub * rawBytes));
+			CVB_CUDA(cudaMemcpy2DAsync(s.raw.p, rawBytes, j.images + f0 * j.framePitch, j.framePitch, rawBytes, nf, cudaMemcpyHostToDevice, st.sCopy));
+			CVB_CUDA(cudaEventRecord(s.evIn, st.sCopy));
+			CVB_CUDA(cudaStreamWaitEvent(s.stream, s.evIn, 0));
+			CVB_CHECK(cvb200_image_to_grayscale_dev(j.pixelFormat, s.raw.as<uint8_t>(), j.width, j.height, j.stride, s.in.as<uint8_t>(), j.stride, nf, rawBytes, j.frameBytes,
+				reinterpret_cast<cvb200_stream_t>(s.stream)));
+		}
 		s.dIn = s.in.as<uint8_t>(); s.inPitch = j.frameBytes;
 	}
 	else {
@@ -210,6 +222,23 @@ DevicePool& device_pool() { static DevicePool p; return p; }
 } // namespace
 
 extern "C" {
+
+int cvb200_canny_kht_process_batch_fmt(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, int pixelFormat, const uint8_t* frames, size_t width, size_t height, size_t stride,
+	size_t batch, size_t framePitchBytes, cvb200_hough_line_t* lines, size_t capacity, size_t* counts)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(canny && hough && frames && counts && width && height && stride >= width && (lines || !capacity), CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(canny->id == CVB200_CANNY_ID && hough->id == CVB200_HOUGHKHT_ID, CVB200_E_INVALID_PARAMETER);
+	if (!batch) return CVB200_S_OK;
+	size_t bpp = 0;
+	CVB_CHECK(cvb200_image_bytes_per_sample(pixelFormat, &bpp));
+	CVB_REQUIRE(framePitchBytes >= stride * bpp * height, CVB200_E_INVALID_PARAMETER); // planar formats: the pitch includes the chroma planes, it cannot be defaulted
+	std::lock_guard<std::mutex> l1(canny->mutex);
+	std::lock_guard<std::mutex> l2(hough->mutex);
+	Job j = { canny, hough, frames, true, width, height, stride, batch, framePitchBytes, lines, capacity, counts, 0, 0 };
+	j.pixelFormat = pixelFormat; j.bpp = bpp;
+	return run_pipeline(j, nullptr);
+}
 
 int cvb200_canny_kht_process_batch_multi(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride,
 	size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts)

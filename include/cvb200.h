@@ -367,9 +367,46 @@ CVB200_API int cvb200_morph_process(const uint8_t* in, size_t width, size_t heig
 CVB200_API int cvb200_morph_process_dev(const uint8_t* in, size_t width, size_t height, size_t stride, const uint8_t* strel, size_t strelWidth, size_t strelHeight, size_t strelStride,
 	uint8_t* out, int opType, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
 
+/* ================================================================================================
+ * 8f-3 -- device-side grayscale of camera frames. Replaces CompVImage::convertGrayscale (base/image/compv_image.cxx:687-692,
+ * base/image/compv_image_conv_to_grayscale.cxx:35-93, compv_image_conv_rgbfamily.cxx:93-120,243-270,400-425).
+ * pixelFormat = the reference's COMPV_SUBTYPE_PIXELS_* value (compv_common.h:347-367); stride in SAMPLES (pixels), as CompVMat::stride().
+ * ============================================================================================== */
+#define CVB200_SUBTYPE_PIXELS_RGB24 13
+#define CVB200_SUBTYPE_PIXELS_BGR24 14
+#define CVB200_SUBTYPE_PIXELS_RGBA32 15
+#define CVB200_SUBTYPE_PIXELS_BGRA32 16
+#define CVB200_SUBTYPE_PIXELS_ABGR32 17
+#define CVB200_SUBTYPE_PIXELS_ARGB32 18
+#define CVB200_SUBTYPE_PIXELS_RGB565LE 19
+#define CVB200_SUBTYPE_PIXELS_RGB565BE 20
+#define CVB200_SUBTYPE_PIXELS_BGR565LE 21
+#define CVB200_SUBTYPE_PIXELS_BGR565BE 22
+#define CVB200_SUBTYPE_PIXELS_Y 25
+#define CVB200_SUBTYPE_PIXELS_NV12 26
+#define CVB200_SUBTYPE_PIXELS_NV21 27
+#define CVB200_SUBTYPE_PIXELS_YUV420P 28
+#define CVB200_SUBTYPE_PIXELS_YVU420P 29
+#define CVB200_SUBTYPE_PIXELS_YUV422P 30
+#define CVB200_SUBTYPE_PIXELS_YUYV422 31
+#define CVB200_SUBTYPE_PIXELS_UYVY422 32
+#define CVB200_SUBTYPE_PIXELS_YUV444P 33
+/* Bytes per sample of the plane that carries luma (3, 4, 2 for the packed formats; 1 for Y / planar / semi-planar YUV, whose Y plane is all that is read).
+ * E_NOT_IMPLEMENTED for the formats the reference cannot convert to gray either (ABGR32, HSV, HSL). */
+CVB200_API int cvb200_image_bytes_per_sample(int pixelFormat, size_t* bytesPerSample);
+/* Host frame in, host gray plane out, same stride in samples (conv_to_grayscale.cxx:213). */
+CVB200_API int cvb200_image_to_grayscale(int pixelFormat, const uint8_t* data, size_t width, size_t height, size_t stride, uint8_t* gray);
+/* Device to device, batched: frame f starts at data + f*framePitchBytes (0 = stride*bytesPerSample*height), its gray plane at gray + f*grayPitch (0 = grayStride*height). */
+CVB200_API int cvb200_image_to_grayscale_dev(int pixelFormat, const uint8_t* data, size_t width, size_t height, size_t stride, uint8_t* gray, size_t grayStride,
+	size_t batch, size_t framePitchBytes, size_t grayPitch, cvb200_stream_t stream);
+
 /* Headline pipeline on host buffers: (optional fused Gaussian) Canny then Hough on `batch` frames; the edge maps stay on the device, only lines return.
  * Equivalent to cvb200_edge_dete_process + cvb200_hough_process per frame (the two calls samples/hough_lines/main.cxx:59,106 makes), pipelined H2D/compute. */
 CVB200_API int cvb200_canny_kht_process_batch(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);
+/* The same call on frames in a camera format (pixelFormat = COMPV_SUBTYPE_PIXELS_*): each frame crosses PCIe once, as it is -- for Y / NV12 / NV21 / I420 / YV12 / 4:2:2 / 4:4:4
+ * planar only its Y plane -- and is made gray on the device (cvb200_image_to_grayscale_dev) in front of the Canny kernels; the reference converts on the CPU first
+ * (CompVImage::convertGrayscale, samples/hough_lines/main.cxx). framePitchBytes = distance between frames in bytes (whole frame incl. chroma planes); stride in samples. */
+CVB200_API int cvb200_canny_kht_process_batch_fmt(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, int pixelFormat, const uint8_t* frames, size_t width, size_t height, size_t stride, size_t batch, size_t framePitchBytes, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);
 /* The same call spread over every device initialised by cvb200_init_devices: frames are independent, the batch is cut into one contiguous shard per device and each
  * shard runs the pipeline above on its device from its own host thread (no collective). Results land in the caller's arrays exactly as with one device. */
 CVB200_API int cvb200_canny_kht_process_batch_multi(cvb200_edge_dete_t* canny, cvb200_hough_t* hough, const uint8_t* images, size_t width, size_t height, size_t stride, size_t batch, size_t framePitch, cvb200_hough_line_t* lines, size_t capacity, size_t* counts);

@@ -317,6 +317,15 @@ def ccl_lsl(which, img, width=None, threads=1, iters=0):
     return out
 
 
+def to_grayscale_ref(subtype, data, width, height, stride, threads=1):
+    """The REFERENCE's CompVImage::wrap + convertGrayscale on a whole frame buffer (bytes) in `subtype` layout; returns the (height, width) gray plane."""
+    r = ref(threads)
+    data = np.ascontiguousarray(data, np.uint8)
+    out = np.zeros((height, width), np.uint8)
+    _chk(r.ref_to_grayscale(int(subtype), _p(data), _sz(width), _sz(height), _sz(stride), _p(out), _sz(width)), "ref_to_grayscale")
+    return out
+
+
 def ccl_lsl_extract_ref(img, blob=True, width=None, threads=1):
     """The REFERENCE's CompVConnectedComponentLabelingResultLSL::extract (ccl_lsl_result.cxx:100-134): list of (n, 2) int16 arrays (x, y), one per label;
     for segments also the boxes the reference derives from them (ccl_lsl_result.cxx:187-230)."""

@@ -444,6 +444,18 @@ int ref_ccl_lsl(const uint8_t* img, size_t w, size_t h, size_t stride, int32_t* 
 	return 0;
 }
 
+// ---- section 8f-3: CompVImage::wrap + CompVImage::convertGrayscale (base/image/compv_image.cxx:381-404, 687-692) ----
+// data: a whole frame in `subtype` layout with `stride` samples per row (planar formats: planes back to back as CompVImage lays them out); gray out with the image's own Y stride.
+int ref_to_grayscale(int subtype, const uint8_t* data, size_t w, size_t h, size_t stride, uint8_t* gray, size_t grayStride)
+{
+	CompVMatPtr image, out;
+	SHIM_CHECK(CompVImage::wrap(static_cast<COMPV_SUBTYPE>(subtype), data, w, h, stride, &image, stride));
+	SHIM_CHECK(CompVImage::convertGrayscale(image, &out));
+	if (out->cols() != w || out->rows() != h) return -2;
+	for (size_t j = 0; j < h; ++j) memcpy(gray + j * grayStride, out->ptr<const uint8_t>(j), w);
+	return 0;
+}
+
 // ---- section 8f-4: the consumers of the PLSL / Hough results ----
 // CompVConnectedComponentLabelingResultLSL::extract (core/ccl/compv_core_ccl_lsl_result.cxx:100-134, 308-416): counts[label] points per label, points (x, y) concatenated in label order.
 // type: 0 = COMPV_CCL_EXTRACT_TYPE_SEGMENT, 1 = COMPV_CCL_EXTRACT_TYPE_BLOB.  Also the boxes computed FROM the extracted segments (ccl_lsl_result.cxx:187-230) when boxesFromSegments != NULL.
