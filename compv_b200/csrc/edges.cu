@@ -577,7 +577,8 @@ int cvb200_edge_dete_set_preblur(cvb200_edge_dete_t* d, size_t size, float sigma
 int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges, size_t batch, size_t framePitch, cudaStream_t stream)
 {
 	CVB_REQUIRE_INIT();
-	CVB_REQUIRE(d && image && edges && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
+	const int stages = d->stages ? d->stages : 7; // 1 = front (or the gmax pass), 2 = hysteresis (or the normalisation pass), 4 = finalize: row-strip mode runs them apart
+	CVB_REQUIRE(d && edges && (image || !(stages & 1) || d->id != CVB200_CANNY_ID) && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
 	CVB_REQUIRE(width <= 0x3fffffff && height <= 0x3fffffff, CVB200_E_OUT_OF_BOUND);
 	if (!framePitch) framePitch = stride * height;
 	d->pendStream = stream; d->pendCheck = false;
@@ -594,9 +595,15 @@ int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, s
 		CVB_REQUIRE(image != edges, CVB200_E_INVALID_PARAMETER);
 		CVB_REQUIRE(static_cast<size_t>(d->taps.ks) <= width && static_cast<size_t>(d->taps.ks) <= height, CVB200_E_INVALID_PARAMETER);
 		CVB_CHECK(d->counters.ensure(batch * sizeof(unsigned int)));
-		unsigned int* gmax = d->counters.as<unsigned int>();
+		unsigned int* gmax = d->externalGmax ? d->externalGmax : d->counters.as<unsigned int>();
 		// `uint16_t gmax = 1` (edge_dete.cxx:93) then max over the frame: the normalisation pass uses max(gmax, 1)
-		CVB_CUDA(cudaMemsetAsync(gmax, 0, batch * sizeof(unsigned int), stream));
+		if (stages & 1) CVB_CUDA(cudaMemsetAsync(gmax, 0, batch * sizeof(unsigned int), stream));
+		if (stages != 7) { // row-strip mode: the two passes apart, the frame maximum is all-reduced (MAX) between them by the caller
+			p.gmaxLanes = d->gmaxLanes ? 1 : 0;
+			if (stages & 1) { p.gmax = gmax; CVB_CHECK(launch_front(p, 2, batch, stream)); }
+			if (stages & 2) { p.gmax = nullptr; p.gmaxIn = gmax; CVB_CHECK(launch_front(p, 3, batch, stream)); }
+			return CVB200_S_OK;
+		}
 		if (d->id == CVB200_SOBEL_ID && d->taps.ks == 3 && !d->genericKernel) { // fast path (canny_fast.cuh): TMA-staged tile, 4 px per lane, both passes
 			FastParams f;
 			memset(&f, 0, sizeof(f));
@@ -655,7 +662,8 @@ int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, s
 		for (int i = 0; i < p.blur.ks; ++i) { if (!(p.blur.k[i] >= 0.f)) tapsOk = false; sum += p.blur.k[i]; }
 		if (!(sum <= 1.003f)) tapsOk = false;
 	}
-	if (!d->genericKernel && tapsOk && p.taps.ks == 3 && (p.blur.ks == 0 || p.blur.ks == 3 || p.blur.ks == 5)) {
+	if (!(stages & 1)) { /* the class map is already in `edges` */ }
+	else if (!d->genericKernel && tapsOk && p.taps.ks == 3 && (p.blur.ks == 0 || p.blur.ks == 3 || p.blur.ks == 5)) {
 		// fast path (canny_fast.cuh): TMA-staged tile, 4 px per lane
 		FastParams f;
 		memset(&f, 0, sizeof(f));
@@ -678,6 +686,7 @@ int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, s
 	h.cls = edges; h.W = p.W; h.H = p.H; h.stride = stride; h.framePitch = framePitch;
 	h.tilesX = tilesX; h.tilesY = tilesY; h.nTiles = static_cast<int>(nTiles);
 	const int rounds = d->hystRounds;
+	if (stages & 2) {
 	CVB_CHECK(d->dirty.ensure(nTiles * 3 * sizeof(int) + (static_cast<size_t>(rounds) + 2) * sizeof(unsigned int)));
 	int* epoch = d->dirty.as<int>();
 	int* lists[2] = { epoch + nTiles, epoch + 2 * nTiles };
@@ -696,6 +705,8 @@ int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, s
 	}
 	CVB_CUDA(cudaMemcpyAsync(d->hostFlag.p, roundCount + rounds + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
 	d->pendCheck = true;
+	}
+	if (!(stages & 4)) return CVB200_S_OK;
 
 	dim3 fg(static_cast<unsigned>(div_up(div_up(width, 16), 128)), static_cast<unsigned>(height), static_cast<unsigned>(batch));
 	CVB_REQUIRE(fg.y <= 65535, CVB200_E_OUT_OF_BOUND);
@@ -724,6 +735,33 @@ int cvb::edge_finish(cvb200_edge_dete* d, bool* again)
 }
 
 extern "C" {
+
+// Row-strip mode: the stages of one detector call apart, so that a caller that owns a strip of a frame (plus halo rows) can exchange what crosses the
+// seams between them.  Canny: 1 = Gaussian/Sobel/NMS -> class map (0, 0x80 weak, 0xff strong) in `edges`; 2 = 8-connected closure of the strong pixels inside `edges` as it
+// stands (halo rows received from the neighbours included); 4 = weak -> 0.  Sobel/Scharr/Prewitt: 1 = frame maximum of |gx|+|gy| into gmax[frame] (device u32),
+// 2 = normalisation with gmax[frame] as given (after the caller's MAX all-reduce).  Synchronous.
+int cvb200_edge_dete_process_stages_dev(cvb200_edge_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges,
+	size_t batch, size_t framePitch, int stages, uint32_t* gmax, cvb200_stream_t stream_)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(d && edges && width && height && stride >= width && stages > 0 && stages <= 7, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(d->id == CVB200_CANNY_ID || (gmax && image && stages <= 3), CVB200_E_INVALID_PARAMETER);
+	if (!batch) return CVB200_S_OK;
+	std::lock_guard<std::mutex> lock(d->mutex);
+	d->stages = stages; d->externalGmax = gmax;
+	int rc = CVB200_S_OK;
+	for (int attempt = 0; attempt < 12; ++attempt) {
+		rc = edge_enqueue(d, image, width, height, stride, edges, batch, framePitch, as_stream(stream_));
+		bool again = false;
+		if (rc == CVB200_S_OK) rc = edge_finish(d, &again);
+		if (rc != CVB200_S_OK || !again) break;
+		// hysteresis did not converge within the rounds issued: promotions are monotone, so simply continue from the map as it stands (never re-run the front here)
+		d->stages = stages & ~1;
+		if (attempt == 11) rc = CVB200_E_INVALID_STATE;
+	}
+	d->stages = 0; d->externalGmax = nullptr;
+	return rc;
+}
 
 int cvb200_edge_dete_process_dev(cvb200_edge_dete_t* d, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges,
 	size_t batch, size_t framePitch, cvb200_stream_t stream_)

@@ -16,6 +16,8 @@ struct cvb200_hough {
 	size_t posCapEl = 0, strCapEl = 0, voteCapEl = 0;   // element capacities of the shared pools (grow-only)
 	double tabRho = 0, tabTheta = 0, tabR = 0; size_t tabNRho = 0;
 	int traceSlot = 0;
+	// SHT row-strip mode (hough_sht.cu): set around one call by the cvb200_hough_sht_* entry points
+	size_t shtFullHeight = 0, shtYOffset = 0; int* shtExternalAcc = nullptr; int shtStage = 0; size_t* shtAccElems = nullptr;
 	size_t pendBatch = 0, pendCapacity = 0; cudaStream_t pendStream = nullptr; // what kht_enqueue left for kht_finish
 	cvb::DevBuf bits, poss, strings, strRev, clus, clusOrd, nClusStr, stack, kern, acc, rowCount, votes, frames, edgeCount, hostIn;
 	cvb::HostBuf hFrames, hVotes, hCounts;

@@ -31,6 +31,7 @@ struct ShtGeom {
 	float fTheta;
 	unsigned int listCap;      // edge list capacity per frame (W*H)
 	unsigned int poolCap;
+	int yOff;                  // row-strip mode: the strip's first row in the full frame (added to y before voting)
 };
 struct ShtDesc { unsigned int base, total; };
 
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) sht_list_kernel(const uint8_t* __restrict
 	if (n) {
 		unsigned int o = sBase + sWarp[warp] + (inc - n);
 		unsigned int* L = list + static_cast<size_t>(f) * g.listCap;
-		const unsigned int yy = static_cast<unsigned int>(y) << 16;
+		const unsigned int yy = static_cast<unsigned int>(y + g.yOff) << 16;
 		#pragma unroll
 		for (int k = 0; k < 4; ++k) if (nz & (1u << k)) L[o++] = yy | static_cast<unsigned int>(x + k);
 	}
@@ -193,6 +194,12 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 	cvb200_hough_line_t* lines, size_t capacity, size_t* counts, cudaStream_t stream)
 {
 	CVB_REQUIRE(h->rho == 1.f && h->theta > 0.f, CVB200_E_INVALID_PARAMETER);
+	// Row-strip mode (cvb200_hough_sht_accumulate_dev / _lines_dev): `height` rows starting at row shtYOffset of a frame of shtFullHeight rows; the accumulator geometry is
+	// the full frame's, stage 1 stops after the voting (the caller sums the strips' accumulators, e.g. with an all-reduce), stage 2 starts from a given accumulator.
+	const size_t stripHeight = height;
+	const int stage = h->shtStage;
+	if (h->shtFullHeight) { CVB_REQUIRE(h->shtYOffset + height <= h->shtFullHeight && batch == 1, CVB200_E_INVALID_PARAMETER); height = h->shtFullHeight; }
+	CVB_REQUIRE(stage == 0 || stage == 3 || (h->shtExternalAcc && batch == 1), CVB200_E_INVALID_PARAMETER);
 	// x*cos16 + y*sin16 must not leave int32 and the rho histogram must fit one SM's shared memory (227 KB)
 	CVB_REQUIRE(width <= 65535 && height <= 65535 && (width + height) <= 29000, CVB200_E_OUT_OF_BOUND);
 	CVB_REQUIRE(batch < 65536 && width * height < (1ull << 31), CVB200_E_OUT_OF_BOUND);
@@ -205,7 +212,8 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 	CVB_REQUIRE(R >= 3 && T >= 1 && T < (1u << 20), CVB200_E_INVALID_PARAMETER);
 	ShtGeom g;
 	memset(&g, 0, sizeof(g));
-	g.W = static_cast<int>(width); g.H = static_cast<int>(height); g.stride = stride; g.framePitch = framePitch;
+	g.W = static_cast<int>(width); g.H = static_cast<int>(stripHeight); g.stride = stride; g.framePitch = framePitch;
+	g.yOff = static_cast<int>(h->shtYOffset);
 	g.R = static_cast<int>(R); g.RP = static_cast<int>((R + 3) & ~static_cast<size_t>(3)); g.T = static_cast<int>(T); g.TW = static_cast<int>(div_up(T, 32));
 	g.barrier = static_cast<int>(width + height);
 	g.thr = static_cast<int>(h->threshold);
@@ -218,7 +226,9 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 		}
 		else { g.cBegin = 0; g.cEnd = static_cast<int>(maxCols); } // generic C++: columns [0, cols-1), column -1 reads the zeroed row padding
 	}
-	g.listCap = static_cast<unsigned int>(width * height);
+	g.listCap = static_cast<unsigned int>(width * stripHeight);
+	if (h->shtAccElems) *h->shtAccElems = T * static_cast<size_t>((R + 3) & ~static_cast<size_t>(3));
+	if (stage == 3) return CVB200_S_OK; // size query only
 
 	// fixed-point tables (initCoords :337-340): same libm, same float accumulation of the angle as the reference
 	std::vector<int32_t> tab(2 * T);
@@ -238,7 +248,8 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 	size_t chunk = (64u << 20) / accFrame;
 	if (chunk < 1) chunk = 1;
 	if (chunk > batch) chunk = batch;
-	CVB_CHECK(h->acc.ensure(chunk * accFrame));
+	if (!h->shtExternalAcc) CVB_CHECK(h->acc.ensure(chunk * accFrame));
+	int* dAcc = h->shtExternalAcc ? h->shtExternalAcc : h->acc.as<int>();
 	CVB_CHECK(h->shtList.ensure(chunk * static_cast<size_t>(g.listCap) * 4));
 	CVB_CHECK(h->shtCursor.ensure((chunk + 1) * 4));
 	CVB_CHECK(h->shtMask.ensure(chunk * R * g.TW * 4));
@@ -263,22 +274,25 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 		for (size_t f0 = 0; f0 < batch; f0 += chunk) {
 			const unsigned int F = static_cast<unsigned int>(std::min(chunk, batch - f0));
 			const uint8_t* e = edges + f0 * framePitch;
-			CVB_CUDA(cudaMemsetAsync(dCursor, 0, F * 4, stream));
-			{
-				dim3 grid(static_cast<unsigned>(div_up(width, 1024)), static_cast<unsigned>(height), F);
-				KernelScope ks_("sht_list", stream);
-				if (aligned4) sht_list_kernel<true><<<grid, 256, 0, stream>>>(e, h->shtList.as<unsigned int>(), dCursor, g);
-				else sht_list_kernel<false><<<grid, 256, 0, stream>>>(e, h->shtList.as<unsigned int>(), dCursor, g);
+			if (stage != 2) {
+				CVB_CUDA(cudaMemsetAsync(dCursor, 0, F * 4, stream));
+				{
+					dim3 grid(static_cast<unsigned>(div_up(width, 1024)), static_cast<unsigned>(stripHeight), F);
+					KernelScope ks_("sht_list", stream);
+					if (aligned4) sht_list_kernel<true><<<grid, 256, 0, stream>>>(e, h->shtList.as<unsigned int>(), dCursor, g);
+					else sht_list_kernel<false><<<grid, 256, 0, stream>>>(e, h->shtList.as<unsigned int>(), dCursor, g);
+				}
+				CVB_LAUNCHED();
+				{ KernelScope ks_("sht_vote", stream);
+				  sht_vote_kernel<<<dim3(static_cast<unsigned>(T), F), 256, smem, stream>>>(h->shtList.as<unsigned int>(), dCursor, dCos, dSin, dAcc, g); }
+				CVB_LAUNCHED();
 			}
-			CVB_LAUNCHED();
-			{ KernelScope ks_("sht_vote", stream);
-			  sht_vote_kernel<<<dim3(static_cast<unsigned>(T), F), 256, smem, stream>>>(h->shtList.as<unsigned int>(), dCursor, dCos, dSin, h->acc.as<int>(), g); }
-			CVB_LAUNCHED();
+			if (stage == 1) { CVB_CUDA(cudaStreamSynchronize(stream)); return CVB200_S_OK; } // the strip's votes are in the caller's accumulator
 			{ KernelScope ks_("sht_nms", stream);
-			  sht_nms_kernel<<<dim3(static_cast<unsigned>(div_up(R, 128)), static_cast<unsigned>(g.TW), F), 128, 0, stream>>>(h->acc.as<int>(), h->shtMask.as<unsigned int>(), g); }
+			  sht_nms_kernel<<<dim3(static_cast<unsigned>(div_up(R, 128)), static_cast<unsigned>(g.TW), F), 128, 0, stream>>>(dAcc, h->shtMask.as<unsigned int>(), g); }
 			CVB_LAUNCHED();
 			{ KernelScope ks_("sht_emit", stream);
-			  sht_emit_kernel<<<F, 1024, 0, stream>>>(h->acc.as<int>(), h->shtMask.as<unsigned int>(), h->shtPool.as<cvb200_hough_line_t>(), dPoolCursor, h->shtDesc.as<ShtDesc>(),
+			  sht_emit_kernel<<<F, 1024, 0, stream>>>(dAcc, h->shtMask.as<unsigned int>(), h->shtPool.as<cvb200_hough_line_t>(), dPoolCursor, h->shtDesc.as<ShtDesc>(),
 				static_cast<int>(f0), g); }
 			CVB_LAUNCHED();
 		}
@@ -314,3 +328,41 @@ int sht_process_dev(cvb200_hough* h, const uint8_t* edges, size_t width, size_t 
 }
 
 } // namespace cvb
+
+// ---- row-strip mode of the SHT: every GPU votes its strip's edge pixels into its own accumulator of the FULL frame's geometry, the accumulators are summed
+// (all-reduce of int32, done by the caller over NCCL), one call turns the sum into lines.  The reference's own thread split is the same sum (houghsht.cxx:455-477). ----
+using namespace cvb;
+extern "C" {
+
+static int sht_strip_call(cvb200_hough_t* h, const uint8_t* edges, size_t width, size_t stripHeight, size_t stride, size_t fullHeight, size_t yOffset, int* acc, int stage, size_t* accElems,
+	cvb200_hough_line_t* lines, size_t capacity, size_t* count, cvb200_stream_t stream)
+{
+	CVB_REQUIRE_INIT();
+	CVB_REQUIRE(h && h->id == CVB200_HOUGHSHT_ID && width && stripHeight && fullHeight, CVB200_E_INVALID_PARAMETER);
+	std::lock_guard<std::mutex> lock(h->mutex);
+	h->shtFullHeight = fullHeight; h->shtYOffset = yOffset; h->shtExternalAcc = acc; h->shtStage = stage; h->shtAccElems = accElems;
+	size_t dummy = 0;
+	const int rc = sht_process_dev(h, edges, width, stripHeight, stride, 1, stride * stripHeight, lines, capacity, count ? count : &dummy, as_stream(stream));
+	h->shtFullHeight = 0; h->shtYOffset = 0; h->shtExternalAcc = nullptr; h->shtStage = 0; h->shtAccElems = nullptr;
+	return rc;
+}
+
+int cvb200_hough_sht_acc_size(cvb200_hough_t* h, size_t width, size_t fullHeight, size_t* elems)
+{
+	CVB_REQUIRE(elems, CVB200_E_INVALID_PARAMETER);
+	return sht_strip_call(h, nullptr, width, fullHeight, width, fullHeight, 0, nullptr, 3, elems, nullptr, 0, nullptr, nullptr);
+}
+
+int cvb200_hough_sht_accumulate_dev(cvb200_hough_t* h, const uint8_t* edges, size_t width, size_t stripHeight, size_t stride, size_t fullHeight, size_t yOffset, int32_t* acc, cvb200_stream_t stream)
+{
+	CVB_REQUIRE(edges && acc, CVB200_E_INVALID_PARAMETER);
+	return sht_strip_call(h, edges, width, stripHeight, stride, fullHeight, yOffset, acc, 1, nullptr, nullptr, 0, nullptr, stream);
+}
+
+int cvb200_hough_sht_lines_dev(cvb200_hough_t* h, int32_t* acc, size_t width, size_t fullHeight, cvb200_hough_line_t* lines, size_t capacity, size_t* count, cvb200_stream_t stream)
+{
+	CVB_REQUIRE(acc && count && (lines || !capacity), CVB200_E_INVALID_PARAMETER);
+	return sht_strip_call(h, nullptr, width, fullHeight, width, fullHeight, 0, acc, 2, nullptr, lines, capacity, count, stream);
+}
+
+} // extern "C"

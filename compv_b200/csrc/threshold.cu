@@ -466,4 +466,34 @@ int cvb200_threshold_adaptive(const uint8_t* in, size_t width, size_t height, si
 	return CVB200_S_OK;
 }
 
+// The Otsu scan on the host for a histogram that was summed elsewhere (row-strip mode: every GPU histograms its strip, the 256 counters are all-reduced).  Same
+// operation order and fp32 arithmetic as otsu_scan_kernel / compv_image_threshold.cxx:77-104 (separate multiplies and divides; x86-64 without -mfma does not contract).
+int cvb200_otsu_threshold_from_histogram(const uint32_t* h, size_t pixelCount, double* threshold)
+{
+	CVB_REQUIRE(h && threshold && pixelCount && pixelCount < (1ull << 31), CVB200_E_INVALID_PARAMETER);
+	const int N = static_cast<int>(pixelCount);
+	unsigned int sum32 = 0;
+	for (unsigned int i = 0; i < 256; ++i) sum32 += i * h[i];
+	const volatile float sumf = static_cast<float>(sum32);
+	volatile float sumB = 0.f, varMax = 0.f;
+	int q1 = 0, q2 = 0, thr = 0;
+	for (int i = 0; i < 256; ++i) {
+		q1 += static_cast<int>(h[i]);
+		if (q1) {
+			q2 = N - q1;
+			if (!q2) break;
+			const volatile float q1f = static_cast<float>(q1), q2f = static_cast<float>(q2);
+			sumB = sumB + static_cast<float>(static_cast<unsigned int>(i) * h[i]);
+			const volatile float a = sumB / q1f, b = (sumf - sumB) / q2f;
+			const volatile float mf = a - b;
+			const volatile float t0 = q1f * q2f;
+			const volatile float t1 = t0 * mf;
+			const volatile float varB = t1 * mf;
+			if (varB > varMax) { varMax = varB; thr = i; }
+		}
+	}
+	*threshold = static_cast<double>(thr);
+	return CVB200_S_OK;
+}
+
 } // extern "C"

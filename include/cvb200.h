@@ -368,6 +368,22 @@ CVB200_API int cvb200_morph_process_dev(const uint8_t* in, size_t width, size_t 
 	uint8_t* out, int opType, int borderType, size_t batch, size_t framePitch, cvb200_stream_t stream);
 
 /* ================================================================================================
+ * 8e -- row-strip mode: one frame cut into horizontal strips, one per GPU (compv_b200/strips.py drives these over torch.distributed / NCCL).
+ * The reference splits the same stages across threads by rows: convolution with overlap rows (compv_math_convlt.h:129-159), Canny NMS + hysteresis per row band
+ * (canny_dete.cxx:175-234, 282-306), SHT accumulation into per-thread accumulators that are summed (houghsht.cxx:455-477).
+ * ============================================================================================== */
+/* Stages of one edge-detector call apart (see edges.cu). Canny: 1 = front -> class map (0 / 0x80 weak / 0xff strong), 2 = closure of the strong pixels inside the map as it
+ * stands, 4 = weak -> 0. Sobel / Scharr / Prewitt: 1 = frame maximum into gmax[frame] (device uint32), 2 = normalisation with gmax[frame] as given. Synchronous. */
+CVB200_API int cvb200_edge_dete_process_stages_dev(cvb200_edge_dete_t* dete, const uint8_t* image, size_t width, size_t height, size_t stride, uint8_t* edges, size_t batch, size_t framePitch, int stages, uint32_t* gmax, cvb200_stream_t stream);
+/* SHT: number of int32 cells of the accumulator of a width x fullHeight frame; votes of a strip (stripHeight rows from row yOffset) into acc (device, zeroed or summed by the
+ * caller afterwards: the kernel OVERWRITES acc with the strip's votes); lines from a (summed) accumulator. */
+CVB200_API int cvb200_hough_sht_acc_size(cvb200_hough_t* hough, size_t width, size_t fullHeight, size_t* elems);
+CVB200_API int cvb200_hough_sht_accumulate_dev(cvb200_hough_t* hough, const uint8_t* edges, size_t width, size_t stripHeight, size_t stride, size_t fullHeight, size_t yOffset, int32_t* acc, cvb200_stream_t stream);
+CVB200_API int cvb200_hough_sht_lines_dev(cvb200_hough_t* hough, int32_t* acc, size_t width, size_t fullHeight, cvb200_hough_line_t* lines, size_t capacity, size_t* count, cvb200_stream_t stream);
+/* Otsu's threshold from a (summed) 256-bin histogram: the scan of CompVImageThreshold::otsu (base/image/compv_image_threshold.cxx:52-100) on the host. */
+CVB200_API int cvb200_otsu_threshold_from_histogram(const uint32_t* histogram256, size_t pixelCount, double* threshold);
+
+/* ================================================================================================
  * 8f-3 -- device-side grayscale of camera frames. Replaces CompVImage::convertGrayscale (base/image/compv_image.cxx:687-692,
  * base/image/compv_image_conv_to_grayscale.cxx:35-93, compv_image_conv_rgbfamily.cxx:93-120,243-270,400-425).
  * pixelFormat = the reference's COMPV_SUBTYPE_PIXELS_* value (compv_common.h:347-367); stride in SAMPLES (pixels), as CompVMat::stride().
