@@ -222,19 +222,11 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 #pragma unroll
 				for (int i = 0; i < 4; ++i) {
 					const int x = xl + i;
-					int gx = hd[a][i] + 2 * hd[b][i] + hd[c][i];
-					int gy = hs[c][i] - hs[a][i];
-					if (!(rowOk && x >= 1 && x < W - 1)) { gx = 0; gy = 0; }
-					const int ax = abs(gx), ay = abs(gy);
-					const int g = ax + ay;
-					unsigned int dir = 0;
-					if (g > tLow) {
-						const int ays = ay << 16;
-						if (ays < kTangentPiOver8Int * ax) dir = 0;
-						else if (ays < kTangentPiTimes3Over8Int * ax) dir = ((gx ^ gy) < 0) ? 2u : 1u;
-						else dir = 3;
-					}
-					packed[i] = static_cast<unsigned int>(g) | (dir << 14);
+					const int gx = hd[a][i] + 2 * hd[b][i] + hd[c][i];
+					const int gy = hs[c][i] - hs[a][i];
+					const int g = abs(gx) + abs(gy);
+					// the NMS direction is NOT computed here: only the few per cent of the pixels with g > tLow need it, stage S4 recomputes gx / gy for those
+					packed[i] = (rowOk && x >= 1 && x < W - 1) ? static_cast<unsigned int>(g) : 0u;
 				}
 				uint2 o;
 				o.x = packed[0] | (packed[1] << 16);
@@ -257,17 +249,26 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 			if (!laneOut || xl >= W) continue;
 			const uint2 gw = *reinterpret_cast<const uint2*>(&sGw[rg * 64 + lane * 2]);
 			unsigned int outw = 0;
-			const unsigned int g4[4] = { gw.x & 0xffffu, gw.x >> 16, gw.y & 0xffffu, gw.y >> 16 };
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				const int gc = static_cast<int>(g4[i] & 0x3fffu);
-				if (gc > tLow) {
-					const unsigned int dir = g4[i] >> 14;
-					const int idx = rg * 128 + lane * 4 + i;
-					const int off = (dir == 0) ? 1 : (dir == 1) ? 129 : (dir == 2) ? -127 : 128;
-					const int n0 = sG[idx - off] & 0x3fff, n1 = sG[idx + off] & 0x3fff;
-					if (!(n0 > gc || n1 > gc)) outw |= static_cast<unsigned int>(gc > tHigh ? CLS_STRONG : CLS_WEAK) << (8 * i);
-				}
+			const int g4[4] = { static_cast<int>(gw.x & 0xffffu), static_cast<int>(gw.x >> 16), static_cast<int>(gw.y & 0xffffu), static_cast<int>(gw.y >> 16) };
+			unsigned int m = (g4[0] > tLow ? 1u : 0u) | (g4[1] > tLow ? 2u : 0u) | (g4[2] > tLow ? 4u : 0u) | (g4[3] > tLow ? 8u : 0u);
+			// candidates only (a few per cent of the pixels): gradient recomputed from the blurred tile, which is still in shared memory, then direction + the two neighbours
+			while (m) {
+				const int i = __ffs(m) - 1;
+				m &= m - 1;
+				const int gc = (i == 0) ? g4[0] : (i == 1) ? g4[1] : (i == 2) ? g4[2] : g4[3];
+				const unsigned char* t = reinterpret_cast<const unsigned char*>(sA + (BKS ? 0 : woff)) + (rg * (BKS ? CF_ROWW : CF_INW) + lane) * 4 + i; // row y-1, my column
+				constexpr int PB = (BKS ? CF_ROWW : CF_INW) * 4;
+				const int a0 = t[-1], a1 = t[0], a2 = t[1], b0 = t[PB - 1], b2 = t[PB + 1], c0 = t[2 * PB - 1], c1 = t[2 * PB], c2 = t[2 * PB + 1];
+				const int gx = (a2 - a0) + 2 * (b2 - b0) + (c2 - c0);
+				const int gy = (c0 + 2 * c1 + c2) - (a0 + 2 * a1 + a2);
+				const int ax = abs(gx), ays = abs(gy) << 16;
+				int off;
+				if (ays < kTangentPiOver8Int * ax) off = 1;
+				else if (ays < kTangentPiTimes3Over8Int * ax) off = ((gx ^ gy) < 0) ? -127 : 129;
+				else off = 128;
+				const int idx = rg * 128 + lane * 4 + i;
+				const int n0 = sG[idx - off], n1 = sG[idx + off];
+				if (!(n0 > gc || n1 > gc)) outw |= static_cast<unsigned int>(gc > tHigh ? CLS_STRONG : CLS_WEAK) << (8 * i);
 			}
 			uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
 			if (p.vecStore && xl + 4 <= W) {
