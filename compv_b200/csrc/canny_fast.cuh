@@ -30,7 +30,9 @@ struct CFGeom {
 	static constexpr int OFF_A = CF_PAD;                                  // input tile, later the blurred tile
 	static constexpr int OFF_M = OFF_A + IN_ROWS * CF_INW + CF_PAD;       // horizontally blurred tile
 	static constexpr int OFF_G = OFF_M + (BKS ? IN_ROWS * CF_ROWW : 0) + CF_PAD; // g|dir (u16 x 128 per row = 64 words)
-	static constexpr int WORDS = OFF_G + G_ROWS * 64 + CF_PAD;
+	static constexpr int OFF_Q = OFF_G + G_ROWS * 64 + CF_PAD;            // per-warp candidate queues of stage S4: 8 warps x (8 rows x 128 px) u16 entries + 8 counters
+	static constexpr int Q_WORDS_PER_WARP = 8 * 128 / 2;
+	static constexpr int WORDS = OFF_Q + CF_WARPS * Q_WORDS_PER_WARP + CF_WARPS + CF_PAD;
 	static constexpr size_t SMEM = WORDS * 4 + 512; // + 128-byte alignment slack, the 32 pad words in front of sA and the mbarrier
 };
 
@@ -238,38 +240,70 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 	__syncthreads();
 
 	// ---- S4: NMS on the unsuppressed g + classification -> global ----
+	// Only a few per cent of the pixels pass g > tLow, and they cluster on a few lanes: testing them where they lie keeps 1-2 lanes of a warp busy for tens of
+	// instructions per row (ncu: 70 of 130 lane-instructions per pixel).  Instead every warp (A) queues the candidates of its rows, (B) works the queue off with all 32
+	// lanes -- gradient recomputed from the blurred tile that is still resident, direction, the two neighbours along it -- writing the class byte into an output tile
+	// (the dead sM), and (C) streams its rows of that tile to global memory.
 	{
 		const unsigned short* sG = reinterpret_cast<const unsigned short*>(sGw);
 		uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
+		unsigned short* q = reinterpret_cast<unsigned short*>(sA + (G::OFF_Q - G::OFF_A)) + warp * (G::Q_WORDS_PER_WARP * 2);
+		unsigned int* qn = sA + (G::OFF_Q - G::OFF_A) + CF_WARPS * G::Q_WORDS_PER_WARP + warp;
+		unsigned int* sOut = BKS ? sM : (sA + (G::OFF_M - G::OFF_A)); // 32 words per output row; without blur sM's slot is unused but absent: see below
+		if (lane == 0) *qn = 0;
+		__syncwarp();
+		// (A)
+		for (int ro = warp; ro < CF_TH; ro += CF_WARPS) {
+			const int rg = ro + 1;
+			const uint2 gw = *reinterpret_cast<const uint2*>(&sGw[rg * 64 + lane * 2]);
+			const int g4[4] = { static_cast<int>(gw.x & 0xffffu), static_cast<int>(gw.x >> 16), static_cast<int>(gw.y & 0xffffu), static_cast<int>(gw.y >> 16) };
+			if (lane >= 1 && lane <= 30) { // lanes 0 and 31 hold halo columns only
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					if (g4[i] > tLow) q[atomicAdd(qn, 1u)] = static_cast<unsigned short>(rg * 128 + lane * 4 + i);
+				}
+			}
+			if (BKS) sOut[ro * CF_ROWW + lane] = 0;
+		}
+		__syncwarp();
+		// (B)
+		const unsigned int n = *qn;
+		constexpr int PB = (BKS ? CF_ROWW : CF_INW) * 4;
+		const unsigned char* tile = reinterpret_cast<const unsigned char*>(sA + (BKS ? 0 : woff));
+		unsigned char* outBytes = reinterpret_cast<unsigned char*>(sOut);
+		for (unsigned int k = lane; k < n; k += 32) {
+			const int idx = q[k];
+			const int rg = idx >> 7, col = idx & 127;
+			const int gc = sG[idx];
+			const unsigned char* t = tile + rg * PB + col; // row y-1, my column
+			const int a0 = t[-1], a1 = t[0], a2 = t[1], b0 = t[PB - 1], b2 = t[PB + 1], c0 = t[2 * PB - 1], c1 = t[2 * PB], c2 = t[2 * PB + 1];
+			const int gx = (a2 - a0) + 2 * (b2 - b0) + (c2 - c0);
+			const int gy = (c0 + 2 * c1 + c2) - (a0 + 2 * a1 + a2);
+			const int ax = abs(gx), ays = abs(gy) << 16;
+			int off;
+			if (ays < kTangentPiOver8Int * ax) off = 1;
+			else if (ays < kTangentPiTimes3Over8Int * ax) off = ((gx ^ gy) < 0) ? -127 : 129;
+			else off = 128;
+			const int n0 = sG[idx - off], n1 = sG[idx + off];
+			if (!(n0 > gc || n1 > gc)) {
+				const uint8_t c = gc > tHigh ? CLS_STRONG : CLS_WEAK;
+				if (BKS) outBytes[(rg - 1) * (CF_ROWW * 4) + col] = c;
+				else { // no blurred tile, hence no spare tile: the few survivors go straight to global memory, after this warp's zero fill below (same warp, ordered by the __syncwarp + fence)
+					const int y = y0 + rg - 1, x = x0 - 4 + col;
+					if (col >= 4 && col < 124 && y < H && x < W) q[k] = static_cast<unsigned short>(idx | (c == CLS_STRONG ? 0x8000 : 0x4000));
+					continue;
+				}
+			}
+			else if (!BKS) q[k] = 0;
+		}
+		__syncwarp();
+		// (C)
 		const bool laneOut = (lane >= 1 && lane <= 30);
 		for (int ro = warp; ro < CF_TH; ro += CF_WARPS) {
 			const int y = y0 + ro;
 			if (y >= H) break; // warp-uniform
-			const int rg = ro + 1;
 			if (!laneOut || xl >= W) continue;
-			const uint2 gw = *reinterpret_cast<const uint2*>(&sGw[rg * 64 + lane * 2]);
-			unsigned int outw = 0;
-			const int g4[4] = { static_cast<int>(gw.x & 0xffffu), static_cast<int>(gw.x >> 16), static_cast<int>(gw.y & 0xffffu), static_cast<int>(gw.y >> 16) };
-			unsigned int m = (g4[0] > tLow ? 1u : 0u) | (g4[1] > tLow ? 2u : 0u) | (g4[2] > tLow ? 4u : 0u) | (g4[3] > tLow ? 8u : 0u);
-			// candidates only (a few per cent of the pixels): gradient recomputed from the blurred tile, which is still in shared memory, then direction + the two neighbours
-			while (m) {
-				const int i = __ffs(m) - 1;
-				m &= m - 1;
-				const int gc = (i == 0) ? g4[0] : (i == 1) ? g4[1] : (i == 2) ? g4[2] : g4[3];
-				const unsigned char* t = reinterpret_cast<const unsigned char*>(sA + (BKS ? 0 : woff)) + (rg * (BKS ? CF_ROWW : CF_INW) + lane) * 4 + i; // row y-1, my column
-				constexpr int PB = (BKS ? CF_ROWW : CF_INW) * 4;
-				const int a0 = t[-1], a1 = t[0], a2 = t[1], b0 = t[PB - 1], b2 = t[PB + 1], c0 = t[2 * PB - 1], c1 = t[2 * PB], c2 = t[2 * PB + 1];
-				const int gx = (a2 - a0) + 2 * (b2 - b0) + (c2 - c0);
-				const int gy = (c0 + 2 * c1 + c2) - (a0 + 2 * a1 + a2);
-				const int ax = abs(gx), ays = abs(gy) << 16;
-				int off;
-				if (ays < kTangentPiOver8Int * ax) off = 1;
-				else if (ays < kTangentPiTimes3Over8Int * ax) off = ((gx ^ gy) < 0) ? -127 : 129;
-				else off = 128;
-				const int idx = rg * 128 + lane * 4 + i;
-				const int n0 = sG[idx - off], n1 = sG[idx + off];
-				if (!(n0 > gc || n1 > gc)) outw |= static_cast<unsigned int>(gc > tHigh ? CLS_STRONG : CLS_WEAK) << (8 * i);
-			}
+			const unsigned int outw = BKS ? sOut[ro * CF_ROWW + lane] : 0u;
 			uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
 			if (p.vecStore && xl + 4 <= W) {
 				*reinterpret_cast<unsigned int*>(o) = outw;
@@ -277,6 +311,17 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 			else {
 #pragma unroll
 				for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+			}
+		}
+		if (!BKS) {
+			__threadfence_block();
+			__syncwarp();
+			for (unsigned int k = lane; k < n; k += 32) {
+				const unsigned int e = q[k];
+				if (e & 0xc000u) {
+					const int idx = e & 0x3fff, rg = idx >> 7, col = idx & 127;
+					cls[static_cast<size_t>(y0 + rg - 1) * p.stride + (x0 - 4 + col)] = (e & 0x8000u) ? CLS_STRONG : CLS_WEAK;
+				}
 			}
 		}
 	}

@@ -28,7 +28,7 @@ struct cvb200_edge_dete {
 	cvb::DevBuf hostIn, hostOut; // staging for the host-buffer entry point
 	bool gmaxLanes;
 	bool genericKernel;     // CVB200_EDGE_SET_BOOL_GENERIC_KERNEL: force the generic front kernel (tests)
-	int hystRounds = 12;    // list-driven hysteresis rounds issued per call after round 0 (raised when a call did not converge)
+	int hystRounds = 8;     // list-driven hysteresis rounds issued per call after round 0 (raised when a call did not converge)
 	int stages = 0; unsigned int* externalGmax = nullptr; // row-strip mode: set around one call by cvb200_edge_dete_process_stages_dev
 	cudaStream_t pendStream = nullptr; bool pendCheck = false; // what edge_enqueue left for edge_finish
 	std::mutex mutex;

@@ -259,7 +259,9 @@ edge_front_kernel(const FrontParams p)
 // ---- hysteresis -------------------------------------------------------------------------------
 constexpr int HT = 64;              // tile edge
 constexpr int HT_THREADS = 256;     // each thread owns a 16-px row segment
-constexpr int HP = HT + 2;          // shared pitch (1-px halo)
+constexpr int HP = HT + 32;         // shared pitch: 16 pad bytes | 64 tile bytes | 16 pad bytes, so that a thread's 16-byte segment is one aligned vector
+constexpr int HX0 = 16;             // column of tile pixel 0 inside a shared row (the 1-px halo sits at HX0 - 1 and HX0 + HT)
+constexpr int HROWS = HT + 2;       // shared rows: halo, 64 tile rows, halo
 
 struct HystParams {
 	uint8_t* cls;
@@ -285,21 +287,36 @@ __device__ __forceinline__ void hysteresis_tile(const HystParams& p, int tile, u
 	const int x0 = tx * HT, y0 = ty * HT;
 	uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
 
-	for (int i = tid; i < HP * HP; i += HT_THREADS) {
-		const int ly = i / HP, lx = i - ly * HP;
-		const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+	// my segment: row ry, columns [16*seg, 16*seg+16): one aligned 16-byte load where the frame allows it
+	const int ry = tid >> 2, seg = tid & 3;
+	uint8_t* row = &s[(ry + 1) * HP + HX0 + seg * 16];
+	unsigned int weak = 0;
+	{
+		const int gy = y0 + ry, gx = x0 + seg * 16;
+		const uint8_t* src = cls + static_cast<size_t>(gy) * p.stride + gx;
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if (gy < p.H && gx + 16 <= p.W && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) v = *reinterpret_cast<const uint4*>(src);
+		else if (gy < p.H) {
+			unsigned int w[4] = { 0, 0, 0, 0 };
+			for (int k = 0; k < 16 && gx + k < p.W; ++k) w[k >> 2] |= static_cast<unsigned int>(src[k]) << (8 * (k & 3));
+			v = make_uint4(w[0], w[1], w[2], w[3]);
+		}
+		*reinterpret_cast<uint4*>(row) = v;
+		// a byte is 0x00, 0x80 (weak) or 0xff (strong): weak <=> bit 7 set and bit 0 clear
+		auto weakBits = [](unsigned int w) { const unsigned int m = (w >> 7) & ~w & 0x01010101u; return (m * 0x01020408u) >> 24; };
+		weak = (weakBits(v.x) & 15u) | ((weakBits(v.y) & 15u) << 4) | ((weakBits(v.z) & 15u) << 8) | ((weakBits(v.w) & 15u) << 12);
+	}
+	// the 1-px halo: top and bottom rows (66 bytes each), left and right columns (64 each)
+	for (int i = tid; i < 2 * (HT + 2) + 2 * HT; i += HT_THREADS) {
+		int ly, lx;
+		if (i < 2 * (HT + 2)) { ly = (i < HT + 2) ? -1 : HT; lx = ((i < HT + 2) ? i : i - (HT + 2)) - 1; }
+		else { const int k = i - 2 * (HT + 2); ly = k & (HT - 1); lx = (k < HT) ? -1 : HT; }
+		const int gx = x0 + lx, gy = y0 + ly;
 		uint8_t v = 0;
 		if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) v = cls[static_cast<size_t>(gy) * p.stride + gx];
-		s[i] = v;
+		s[(ly + 1) * HP + HX0 + lx] = v;
 	}
 	__syncthreads();
-
-	// my segment: row ry, columns [16*seg, 16*seg+16)
-	const int ry = tid >> 2, seg = tid & 3;
-	uint8_t* row = &s[(ry + 1) * HP + 1 + seg * 16];
-	unsigned int weak = 0;
-#pragma unroll
-	for (int k = 0; k < 16; ++k) if (row[k] == CLS_WEAK) weak |= (1u << k);
 	unsigned int promoted = 0;
 
 	// Chaotic relaxation: a thread reads its neighbours' cells while their owners may be promoting them (compute-sanitizer racecheck reports exactly this
@@ -366,7 +383,7 @@ template <bool FIRST>
 __global__ void __launch_bounds__(HT_THREADS)
 canny_hysteresis_kernel(const HystParams p)
 {
-	__shared__ uint8_t s[HP * HP];
+	__shared__ __align__(16) uint8_t s[HROWS * HP];
 	__shared__ int sBorder;
 	if (FIRST) { hysteresis_tile(p, blockIdx.x, s, &sBorder); return; }
 	const unsigned int n = *p.countIn;
