@@ -27,6 +27,12 @@ FAST_SET_INT_FAST_TYPE = 4
 FAST_SET_BOOL_NON_MAXIMA_SUPP = 5
 FAST_TYPE_9 = 6
 FAST_TYPE_12 = 7
+ORB_ID = 8
+ORB_SET_INT_INTERNAL_DETE_ID = 9
+ORB_SET_INT_FAST_THRESHOLD = 10
+ORB_SET_BOOL_FAST_NON_MAXIMA_SUPP = 11
+ORB_SET_INT_PYRAMID_LEVELS = 12
+ORB_SET_INT_MAX_FEATURES = 15
 EDGE_SET_BOOL_X86_SSE41_GMAX_LANES = 1000
 EDGE_SET_BOOL_GENERIC_KERNEL = 1001
 HOUGH_SET_BOOL_X86_SIMD_SCAN = 1002

@@ -295,6 +295,10 @@ struct cvb200_corner_dete {
 	int N;
 	int maxFeatures;     // 2000
 	bool nms;            // true
+	// ORB detector (id CVB200_ORB_ID): its own quota + the internal FAST object (which keeps FAST's defaults, maxFeatures 2000 included)
+	int orbMaxFeatures = 2000;
+	cvb200_corner_dete* orbFast = nullptr;
+	DevBuf orbLevel, orbPts, orbMom;
 	DevBuf mask, prefix, list, counters, hostIn, points;
 	HostBuf hostCount;
 	std::mutex mutex;
@@ -356,16 +360,161 @@ static int fast_launch(cvb200_corner_dete* d, const uint8_t* image, size_t width
 	return CVB200_S_OK;
 }
 
+// ---- the ORB detector (core/features/orb/compv_core_feature_orb_dete.cxx:148-358) on top of the FAST kernels ----
+// Pyramid level: CompVImage::scale from the ORIGINAL image with the reference's 8-bit fixed-point bilinear kernel (base/image/compv_image_scale_bilinear.cxx:50-86, factors :163-176).
+__global__ void orb_scale_bilinear_kernel(const uint8_t* __restrict__ in, int inStride, uint8_t* __restrict__ out, int outW, int outH, int outStride, unsigned int sfx, unsigned int sfy)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+	if (i >= outW) return;
+	const unsigned int oy = static_cast<unsigned int>(j) * sfy, x = static_cast<unsigned int>(i) * sfx;
+	const uint8_t* p = in + static_cast<size_t>(oy >> 8) * inStride + (x >> 8);
+	const unsigned int y0 = oy & 255u, y1 = 255u - y0, x0 = x & 255u, x1 = 255u - x0;
+	const unsigned int n0 = p[0], n1 = p[1], n2 = p[inStride], n3 = p[inStride + 1];
+	out[static_cast<size_t>(j) * outStride + i] = static_cast<uint8_t>(((y1 * ((n0 * x1) + (n1 * x0))) >> 16) + ((y0 * ((n2 * x1) + (n3 * x0))) >> 16));
+}
+
+// Intensity-centroid moments of the circular patch (base/compv_patch.cxx:96-140; abscissas :199-203): m10 = sum i*I, m01 = sum j*I over the disc.  One warp per point,
+// one lane per patch row; integer sums, so the order is free.
+struct OrbAbscissas { short dx[64]; };
+__global__ void orb_moments_kernel(const uint8_t* __restrict__ img, int stride, const int2* __restrict__ centres, int n, int radius, OrbAbscissas ab, int2* __restrict__ moments)
+{
+	const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (pt >= n) return;
+	const int2 c = centres[pt];
+	int m10 = 0, m01 = 0;
+	for (int j = -radius + lane; j <= radius; j += 32) {
+		const int dX = ab.dx[j < 0 ? -j : j];
+		const uint8_t* row = img + static_cast<size_t>(c.y + j) * stride + c.x;
+		int s = 0, si = 0;
+		for (int i = -dX; i <= dX; ++i) { const int v = row[i]; s += v; si += i * v; }
+		m10 += si; m01 += j * s;
+	}
+	for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+	if (lane == 0) moments[pt] = make_int2(m10, m01);
+}
+
+// CompVInterestPoint::selectBest (compv_common.h:641-655): the same libstdc++ nth_element + partition on the same list, so ties at the cut resolve as in the reference
+static void select_best(std::vector<cvb200_interest_point_t>& v, size_t max)
+{
+	if (max > 1) {
+		std::nth_element(v.begin(), v.begin() + max, v.end(), [](const cvb200_interest_point_t& i, const cvb200_interest_point_t& j) { return i.strength > j.strength; });
+		const float pivot = v.at(max - 1).strength;
+		v.resize(std::partition(v.begin() + max, v.end(), [pivot](cvb200_interest_point_t i) { return i.strength >= pivot; }) - v.begin());
+	}
+}
+
+// FAST on a device image, points to the host with FAST's own maxFeatures applied (what CompVCornerDeteFAST::process returns, fast_dete.cxx:163-422)
+static int fast_points_from_dev(cvb200_corner_dete* d, const uint8_t* dImage, size_t width, size_t height, size_t stride, std::vector<cvb200_interest_point_t>& v)
+{
+	const size_t devCap = d->nms ? (width * height) / 4 + 16 : width * height;
+	CVB_CHECK(d->points.ensure(devCap * sizeof(cvb200_interest_point_t) + sizeof(unsigned int)));
+	CVB_CHECK(d->hostCount.ensure(sizeof(unsigned int)));
+	cvb200_interest_point_t* dPts = d->points.as<cvb200_interest_point_t>();
+	unsigned int* dCount = reinterpret_cast<unsigned int*>(dPts + devCap);
+	CVB_CHECK(fast_launch(d, dImage, width, height, stride, 1, stride * height, nullptr, dPts, devCap, dCount, d->threshold, d->N, d->nms, 0));
+	unsigned int* hCount = d->hostCount.as<unsigned int>();
+	CVB_CUDA(cudaMemcpyAsync(hCount, dCount, sizeof(unsigned int), cudaMemcpyDeviceToHost, 0));
+	CVB_CUDA(cudaStreamSynchronize(0));
+	const size_t found = *hCount;
+	CVB_REQUIRE(found <= devCap, CVB200_E_OUT_OF_BOUND);
+	v.resize(found);
+	if (found) CVB_CUDA(cudaMemcpy(v.data(), dPts, found * sizeof(cvb200_interest_point_t), cudaMemcpyDeviceToHost));
+	if (d->maxFeatures > 1 && found > static_cast<size_t>(d->maxFeatures)) select_best(v, static_cast<size_t>(d->maxFeatures));
+	return CVB200_S_OK;
+}
+
+static int orb_process(cvb200_corner_dete* d, const uint8_t* image, size_t width, size_t height, size_t stride, cvb200_interest_point_t* points, size_t capacity, size_t* count)
+{
+	constexpr int kLevels = 8, kPatchDiameter = 31, kRadius = kPatchDiameter >> 1; // orb_dete.cxx:35-44
+	const float kSf = 0.83f;
+	float sfTab[kLevels], sfs = 1.f;                                             // compv_image_scale_pyramid.cxx:37-45
+	sfTab[0] = 1.f;
+	{ float s = kSf; for (int l = 1; l < kLevels; ++l, s *= kSf) { sfTab[l] = s; sfs += s; } }
+	OrbAbscissas ab;
+	memset(&ab, 0, sizeof(ab));
+	for (int i = 0; i <= kRadius; ++i) ab.dx[i] = static_cast<short>(sqrt(static_cast<double>(kRadius * kRadius - (i * i)))); // compv_patch.cxx:199-203
+	cvb200_corner_dete* f = d->orbFast;
+	f->threshold = d->threshold; f->nms = d->nms; f->type = d->type; f->N = d->N;   // initDetector (orb_dete.cxx:263-273); FAST's own maxFeatures stays at its default
+	const size_t n = stride * height;
+	CVB_CHECK(d->hostIn.ensure(n + stride + 16));
+	CVB_CUDA(cudaMemcpyAsync(d->hostIn.p, image, n, cudaMemcpyHostToDevice, 0));
+	std::vector<cvb200_interest_point_t> all, pts;
+	for (int level = 0; level < kLevels; ++level) {
+		const float sf = sfTab[level];
+		const uint8_t* dImg = d->hostIn.as<uint8_t>();
+		size_t lw = width, lh = height, ls = stride;
+		if (level) {
+			lw = static_cast<size_t>(width * sf); lh = static_cast<size_t>(height * sf); ls = (lw + 15) & ~static_cast<size_t>(15);
+			if (lw < 4 || lh < 4) continue;
+			CVB_CHECK(d->orbLevel.ensure(ls * lh));
+			const float fsx = static_cast<float>(width) / lw, fsy = static_cast<float>(height) / lh;
+			const unsigned int sfx = static_cast<unsigned int>(static_cast<long>(fsx * 256.f)), sfy = static_cast<unsigned int>(static_cast<long>(fsy * 256.f));
+			{
+				KernelScope ks_("orb_scale", 0);
+				orb_scale_bilinear_kernel<<<dim3(static_cast<unsigned>(div_up(lw, 256)), static_cast<unsigned>(lh)), 256>>>(d->hostIn.as<uint8_t>(), static_cast<int>(stride), d->orbLevel.as<uint8_t>(),
+					static_cast<int>(lw), static_cast<int>(lh), static_cast<int>(ls), sfx, sfy);
+			}
+			CVB_LAUNCHED();
+			dImg = d->orbLevel.as<uint8_t>();
+		}
+		CVB_CHECK(fast_points_from_dev(f, dImg, lw, lh, ls, pts));
+		if (d->orbMaxFeatures > 0 && !pts.empty()) {                              // orb_dete.cxx:312-320
+			const float nf = ((d->orbMaxFeatures / sfs) * sf);
+			int32_t mf = static_cast<int32_t>(nf + 0.5);
+			mf = mf < 10 ? 10 : mf;
+			if (pts.size() > static_cast<size_t>(mf)) select_best(pts, static_cast<size_t>(mf));
+		}
+		{                                                                         // eraseTooCloseToBorder (compv_common.h:657-663), border (31 + 5) >> 1
+			const float fw = static_cast<float>(lw), fh = static_cast<float>(lh), b = static_cast<float>((kPatchDiameter + 5) >> 1);
+			pts.erase(std::remove_if(pts.begin(), pts.end(), [&](const cvb200_interest_point_t& q) { return (q.x < b || (q.x + b) >= fw || (q.y < b) || (q.y + b) >= fh); }), pts.end());
+		}
+		if (pts.empty()) continue;
+		// moments on the device, on the level image that is already there
+		std::vector<int2> centres(pts.size()), mom(pts.size());
+		for (size_t k = 0; k < pts.size(); ++k) {
+			centres[k].x = static_cast<int>(static_cast<int>(pts[k].x >= 0.0 ? (pts[k].x + 0.5) : (pts[k].x - 0.5)));
+			centres[k].y = static_cast<int>(static_cast<int>(pts[k].y >= 0.0 ? (pts[k].y + 0.5) : (pts[k].y - 0.5)));
+		}
+		CVB_CHECK(d->orbPts.ensure(pts.size() * sizeof(int2)));
+		CVB_CHECK(d->orbMom.ensure(pts.size() * sizeof(int2)));
+		CVB_CUDA(cudaMemcpyAsync(d->orbPts.p, centres.data(), pts.size() * sizeof(int2), cudaMemcpyHostToDevice, 0));
+		{
+			KernelScope ks_("orb_moments", 0);
+			orb_moments_kernel<<<static_cast<unsigned>(div_up(pts.size(), 8)), 256>>>(dImg, static_cast<int>(ls), d->orbPts.as<int2>(), static_cast<int>(pts.size()), kRadius, ab, d->orbMom.as<int2>());
+		}
+		CVB_LAUNCHED();
+		CVB_CUDA(cudaMemcpy(mom.data(), d->orbMom.p, pts.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+		const float sfi = 1.f / sf, patchSize = kPatchDiameter / sf;
+		for (size_t k = 0; k < pts.size(); ++k) {                                 // orb_dete.cxx:330-355; atan2f of the host's libm, as in the reference
+			cvb200_interest_point_t& q = pts[k];
+			q.level = level; q.size = patchSize;
+			const float rad = std::atan2(static_cast<float>(mom[k].y), static_cast<float>(mom[k].x));
+			q.orient = static_cast<float>(rad * (180.f / 3.1415926535897932384626433f));
+			if (q.orient < 0) q.orient += 360;
+			if (level != 0) { q.x *= sfi; q.y *= sfi; }
+		}
+		all.insert(all.end(), pts.begin(), pts.end());
+	}
+	*count = all.size();
+	if (capacity && !all.empty()) memcpy(points, all.data(), std::min(capacity, all.size()) * sizeof(cvb200_interest_point_t));
+	return (capacity && all.size() > capacity) ? CVB200_E_OUT_OF_BOUND : CVB200_S_OK;
+}
+
 extern "C" {
 
 int cvb200_corner_dete_new(cvb200_corner_dete_t** dete, int id)
 {
 	CVB_REQUIRE(dete, CVB200_E_INVALID_PARAMETER);
 	CVB_REQUIRE_INIT();
-	CVB_REQUIRE(id == CVB200_FAST_ID, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(id == CVB200_FAST_ID || id == CVB200_ORB_ID, CVB200_E_INVALID_PARAMETER);
 	cvb200_corner_dete* d = new (std::nothrow) cvb200_corner_dete();
 	CVB_REQUIRE(d, CVB200_E_OUT_OF_MEMORY);
-	d->id = id; d->threshold = 20; d->type = CVB200_FAST_TYPE_9; d->N = 9; d->maxFeatures = 2000; d->nms = true; // fast_dete.cxx:74-80,111-125
+	d->id = id; d->threshold = 20; d->type = CVB200_FAST_TYPE_9; d->N = 9; d->maxFeatures = 2000; d->nms = true; // fast_dete.cxx:74-80,111-125 (ORB: orb_dete.cxx:35-44)
+	if (id == CVB200_ORB_ID) {
+		d->orbFast = new (std::nothrow) cvb200_corner_dete();
+		if (!d->orbFast) { delete d; return CVB200_E_OUT_OF_MEMORY; }
+		d->orbFast->id = CVB200_FAST_ID; d->orbFast->threshold = 20; d->orbFast->type = CVB200_FAST_TYPE_9; d->orbFast->N = 9; d->orbFast->maxFeatures = 2000; d->orbFast->nms = true;
+	}
 	*dete = d;
 	return CVB200_S_OK;
 }
@@ -374,6 +523,8 @@ int cvb200_corner_dete_free(cvb200_corner_dete_t** dete)
 {
 	if (dete && *dete) {
 		cvb200_corner_dete* d = *dete;
+		if (d->orbFast) { cvb200_corner_dete_t* f = d->orbFast; cvb200_corner_dete_free(&f); }
+		d->orbLevel.release(); d->orbPts.release(); d->orbMom.release();
 		d->mask.release(); d->prefix.release(); d->list.release(); d->counters.release(); d->hostIn.release(); d->points.release(); d->hostCount.release();
 		delete d;
 		*dete = nullptr;
@@ -385,6 +536,21 @@ int cvb200_corner_dete_free(cvb200_corner_dete_t** dete)
 int cvb200_corner_dete_set(cvb200_corner_dete_t* d, int id, const void* valuePtr, size_t valueSize)
 {
 	CVB_REQUIRE(d && valuePtr && valueSize, CVB200_E_INVALID_PARAMETER);
+	if (d->id == CVB200_ORB_ID) { // orb_dete.cxx:58-134
+		switch (id) {
+		case CVB200_ORB_SET_INT_FAST_THRESHOLD: CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER); { const int t = *static_cast<const int*>(valuePtr); d->threshold = t < 0 ? 0 : (t > 255 ? 255 : t); } return CVB200_S_OK;
+		case CVB200_ORB_SET_BOOL_FAST_NON_MAXIMA_SUPP: CVB_REQUIRE(valueSize == sizeof(bool), CVB200_E_INVALID_PARAMETER); d->nms = *static_cast<const bool*>(valuePtr); return CVB200_S_OK;
+		case CVB200_ORB_SET_INT_MAX_FEATURES: CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER); d->orbMaxFeatures = *static_cast<const int*>(valuePtr); return CVB200_S_OK;
+		case CVB200_ORB_SET_INT_INTERNAL_DETE_ID: {
+			CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
+			const int t = *static_cast<const int*>(valuePtr);
+			CVB_REQUIRE(t == CVB200_FAST_TYPE_9 || t == CVB200_FAST_TYPE_12, CVB200_E_INVALID_PARAMETER);
+			d->type = t; d->N = (t == CVB200_FAST_TYPE_12) ? 12 : 9;
+			return CVB200_S_OK;
+		}
+		default: return CVB200_E_NOT_IMPLEMENTED; // pyramid levels / scale factor / scale type: the reference rebuilds its pyramid with scaleFactor() of LEVEL 0, i.e. 1.0 (orb_dete.cxx:101,121): not reproduced
+		}
+	}
 	switch (id) {
 	case CVB200_FAST_SET_INT_THRESHOLD: {
 		CVB_REQUIRE(valueSize == sizeof(int), CVB200_E_INVALID_PARAMETER);
@@ -417,6 +583,7 @@ int cvb200_corner_dete_process_dev(cvb200_corner_dete_t* d, const uint8_t* image
 {
 	CVB_REQUIRE_INIT();
 	CVB_REQUIRE(d && image && points && counts && capacity && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
+	CVB_REQUIRE(d->id == CVB200_FAST_ID, CVB200_E_NOT_IMPLEMENTED); // the ORB detector has the per-frame entry point only
 	CVB_REQUIRE(capacity < (1ull << 32), CVB200_E_OUT_OF_BOUND);
 	if (!batch) return CVB200_S_OK;
 	if (!framePitch) framePitch = stride * height;
@@ -433,6 +600,7 @@ int cvb200_corner_dete_process(cvb200_corner_dete_t* d, const uint8_t* image, si
 	*count = 0;
 	CVB_REQUIRE(width >= 4 && height >= 4, CVB200_E_INVALID_PARAMETER);
 	std::lock_guard<std::mutex> lock(d->mutex);
+	if (d->id == CVB200_ORB_ID) return orb_process(d, image, width, height, stride, points, capacity, count);
 	const size_t n = stride * height;
 	// device capacity: enough for every possible corner so that selectBest sees the full list like the reference does
 	size_t devCap = d->nms ? (width * height) / 4 + 16 : width * height;

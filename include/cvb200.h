@@ -47,6 +47,16 @@ extern "C" {
 /* ---- feature ids and capability ids: numeric values of the anonymous enum in
  *      base/include/compv/base/compv_features.h:47-121 and base/include/compv/base/compv_ccl.h:61-103 ---- */
 #define CVB200_FAST_ID                                  1
+/* 8f-2: the ORB detector (core/features/orb/compv_core_feature_orb_dete.cxx): same object type and calls as FAST (cvb200_corner_dete_new(&d, CVB200_ORB_ID), _set, _process);
+ * defaults of the reference (8 levels at 0.83, FAST9 threshold 20 + NMS, 2000 features, patch 31). Values = COMPV_ORB_* (compv_features.h:60-72). */
+#define CVB200_ORB_ID 8
+#define CVB200_ORB_SET_INT_INTERNAL_DETE_ID 9
+#define CVB200_ORB_SET_INT_FAST_THRESHOLD 10
+#define CVB200_ORB_SET_BOOL_FAST_NON_MAXIMA_SUPP 11
+#define CVB200_ORB_SET_INT_PYRAMID_LEVELS 12
+#define CVB200_ORB_SET_INT_PYRAMID_SCALE_TYPE 13
+#define CVB200_ORB_SET_FLT32_PYRAMID_SCALE_FACTOR 14
+#define CVB200_ORB_SET_INT_MAX_FEATURES 15
 #define CVB200_FAST_SET_INT_THRESHOLD                   2
 #define CVB200_FAST_SET_INT_MAX_FEATURES                3
 #define CVB200_FAST_SET_INT_FAST_TYPE                   4

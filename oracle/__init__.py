@@ -244,6 +244,32 @@ def fast_detect(which, img, N=9, threshold=20, nms=True, max_features=-1, width=
     return (out, ms[:iters]) if iters else out
 
 
+def orb_detect(which, img, threshold=20, nms=True, max_features=2000, n=9, width=None, threads=1, iters=0):
+    """The ORB DETECTOR (pyramid of 8 levels at 0.83, FAST per level, per-level quota, orientation): points in the reference's order (level by level)."""
+    w, h, stride = _frame_args(img, width)
+    cap = 1 << 16
+    pts = np.zeros(cap, POINT_DTYPE)
+    cnt = C.c_size_t(0)
+    if which == "orc":
+        _chk(orc().orc_orb_detect(_p(img), _sz(w), _sz(h), _sz(stride), int(threshold), int(bool(nms)), int(n), int(max_features), _p(pts), _sz(cap), C.byref(cnt)), "orc_orb_detect")
+        return pts[:cnt.value].copy()
+    ms = np.zeros(max(iters, 1), np.float64)
+    _chk(ref(threads).ref_orb_detect(_p(img), _sz(w), _sz(h), _sz(stride), int(threshold), int(bool(nms)), int(max_features), _p(pts), _sz(cap), C.byref(cnt), int(iters), _p(ms)), "ref_orb_detect")
+    out = pts[:cnt.value].copy()
+    return (out, ms[:iters]) if iters else out
+
+
+def scale_bilinear(which, img, out_w, out_h, width=None):
+    """CompVImage::scale(..., COMPV_INTERPOLATION_TYPE_BILINEAR): 8-bit fixed-point bilinear kernel."""
+    w, h, stride = _frame_args(img, width)
+    out = np.zeros((out_h, out_w), np.uint8)
+    if which == "orc":
+        _chk(orc().orc_scale_bilinear(_p(img), _sz(w), _sz(h), _sz(stride), _p(out), _sz(out_w), _sz(out_h), _sz(out_w)), "orc_scale_bilinear")
+    else:
+        _chk(ref(1).ref_scale_bilinear(_p(img), _sz(w), _sz(h), _sz(stride), _p(out), _sz(out_w), _sz(out_h)), "ref_scale_bilinear")
+    return out
+
+
 LINE_DTYPE = np.dtype([("rho", np.float32), ("theta", np.float32), ("strength", np.uint64)])
 
 

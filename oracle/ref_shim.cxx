@@ -238,6 +238,40 @@ int ref_fast_detect(const uint8_t* img, size_t w, size_t h, size_t stride, int f
 	return 0;
 }
 
+// ---- section 8f-2: the ORB detector through the factory (core/features/orb/compv_core_feature_orb_dete.cxx:148-358), defaults except what is passed ----
+int ref_orb_detect(const uint8_t* img, size_t w, size_t h, size_t stride, int fastThreshold, int nms, int maxFeatures, void* pts, size_t capacity, size_t* count, int iters, double* msOut)
+{
+	CompVMatPtr image;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	CompVCornerDetePtr dete;
+	SHIM_CHECK(CompVCornerDete::newObj(&dete, COMPV_ORB_ID));
+	SHIM_CHECK(dete->setInt(COMPV_ORB_SET_INT_FAST_THRESHOLD, fastThreshold));
+	SHIM_CHECK(dete->setBool(COMPV_ORB_SET_BOOL_FAST_NON_MAXIMA_SUPP, nms != 0));
+	SHIM_CHECK(dete->setInt(COMPV_ORB_SET_INT_MAX_FEATURES, maxFeatures));
+	CompVInterestPointVector points;
+	SHIM_CHECK(dete->process(image, points));
+	for (int it = 0; it < iters; ++it) {
+		const double t0 = now_ms();
+		SHIM_CHECK(dete->process(image, points));
+		if (msOut) msOut[it] = now_ms() - t0;
+	}
+	*count = points.size();
+	if (pts && capacity) memcpy(pts, points.data(), (points.size() < capacity ? points.size() : capacity) * sizeof(CompVInterestPoint));
+	return 0;
+}
+
+// CompVImage::scale, bilinear (base/image/compv_image.cxx:840-905, base/image/compv_image_scale_bilinear.cxx)
+int ref_scale_bilinear(const uint8_t* img, size_t w, size_t h, size_t stride, uint8_t* out, size_t outW, size_t outH)
+{
+	CompVMatPtr image, scaled;
+	int r = wrap8u(img, w, h, stride, &image);
+	if (r) return r;
+	SHIM_CHECK(CompVImage::scale(image, &scaled, outW, outH, COMPV_INTERPOLATION_TYPE_BILINEAR));
+	for (size_t j = 0; j < outH; ++j) memcpy(out + j * outW, scaled->ptr<const uint8_t>(j), outW);
+	return 0;
+}
+
 // ---- a6/a7: CompVHough (SHT / KHT) through the factory (base/compv_features.cxx:176-191) ----
 // which: 0 = COMPV_HOUGHSHT_ID, 1 = COMPV_HOUGHKHT_ID. theta is what CompVHough::newObj receives (KHT: degrees; SHT: see houghsht.cxx).
 // lines layout == CompVHoughLine {float rho; float theta; size_t strength}. iters > 0 adds a timed loop (ms per iteration in msOut, may be NULL).

@@ -1,0 +1,72 @@
+"""the ORB detector (core/features/orb/compv_core_feature_orb_dete.cxx:148-358) -- pyramid (8 levels, 0.83, fixed-point bilinear from the original image),
+FAST9 + NMS per level, per-level quota, border erase, intensity-centroid orientation.  The restatement (oracle/compv_oracle_orb.cpp) is pinned on the compiled reference,
+every field bit for bit (CPU); the CUDA path is compared with it the same way (GPU)."""
+import numpy as np
+import pytest
+
+import oracle
+from frames import frame_g, frame_smooth, frame_text, frame_const
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+FIELDS = ("x", "y", "strength", "orient", "level", "size")
+
+
+def frames(w, h):
+    return [frame_g(w, h, 77), frame_smooth(w, h, 5), frame_text(w, h, 2)]
+
+
+def same_points(a, b):
+    assert len(a) == len(b)
+    for k in FIELDS:
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h", [(640, 480), (321, 243), (1920, 1080)])
+def test_oracle_bilinear_scale_vs_reference(w, h):
+    img = frame_g(w, h, 9)
+    for (ow, oh) in [(int(w * 0.83), int(h * 0.83)), (int(w * 0.27), int(h * 0.27)), (w // 2, h // 3)]:
+        np.testing.assert_array_equal(oracle.scale_bilinear("orc", img, ow, oh), oracle.scale_bilinear("ref", img, ow, oh))
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h", [(640, 480), (321, 243), (1280, 720)])
+@pytest.mark.parametrize("max_features", [2000, 300, -1])
+def test_oracle_orb_vs_reference(w, h, max_features):
+    for img in frames(w, h):
+        a = oracle.orb_detect("orc", img, max_features=max_features)
+        same_points(a, oracle.orb_detect("ref", img, max_features=max_features, threads=1))
+        if len(a):
+            assert a["level"].min() == 0 and a["level"].max() <= 7 and (a["orient"] >= 0).all() and (a["orient"] < 360).all()
+
+
+@needs_ref
+def test_oracle_orb_threshold_and_empty():
+    img = frame_g(640, 480, 3)
+    same_points(oracle.orb_detect("orc", img, threshold=40, nms=False), oracle.orb_detect("ref", img, threshold=40, nms=False, threads=1))
+    assert len(oracle.orb_detect("orc", frame_const(320, 200, 90))) == len(oracle.orb_detect("ref", frame_const(320, 200, 90), threads=1)) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(640, 480), (321, 243), (1920, 1080)])
+@pytest.mark.parametrize("max_features", [2000, 300, -1])
+def test_cuda_orb(cvb, w, h, max_features):
+    from compv_b200 import _ffi
+    d = cvb.CompVCornerDete.newObj(_ffi.ORB_ID)
+    d.setInt(_ffi.ORB_SET_INT_MAX_FEATURES, max_features)
+    for img in frames(w, h):
+        same_points(d.process(img), oracle.orb_detect("orc", img, max_features=max_features))
+
+
+@pytest.mark.gpu
+def test_cuda_orb_caps(cvb):
+    import ctypes
+    from compv_b200 import _ffi
+    img = frame_g(640, 480, 3)
+    d = cvb.CompVCornerDete.newObj(_ffi.ORB_ID)
+    d.setInt(_ffi.ORB_SET_INT_FAST_THRESHOLD, 40)
+    d.setBool(_ffi.ORB_SET_BOOL_FAST_NON_MAXIMA_SUPP, False)
+    same_points(d.process(img), oracle.orb_detect("orc", img, threshold=40, nms=False))
+    assert d.set(_ffi.ORB_SET_INT_FAST_THRESHOLD, 1.0, ctypes.c_double) == _ffi.E_INVALID_PARAMETER          # size check, orb_dete.cxx:62
+    assert d.set(_ffi.ORB_SET_INT_PYRAMID_LEVELS, 4, ctypes.c_int32) == _ffi.E_NOT_IMPLEMENTED
+    assert len(d.process(frame_const(320, 200, 90))) == 0
