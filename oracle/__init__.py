@@ -259,6 +259,19 @@ def orb_detect(which, img, threshold=20, nms=True, max_features=2000, n=9, width
     return (out, ms[:iters]) if iters else out
 
 
+def fast_detect_after_ref(img_a, img_b):
+    """Reference defect probe (see ref_shim.cxx ref_fast_detect_after): FAST on img_b with a detector that has just processed img_a.  Returns (points, shared_stride)."""
+    r = ref(1)
+    ha, wa = img_a.shape
+    hb, wb = img_b.shape
+    pts = np.zeros(wb * hb, POINT_DTYPE)
+    cnt = C.c_size_t(0)
+    rc = r.ref_fast_detect_after(_p(np.ascontiguousarray(img_a)), _sz(wa), _sz(ha), _p(np.ascontiguousarray(img_b)), _sz(wb), _sz(hb), _p(pts), _sz(len(pts)), C.byref(cnt))
+    if rc not in (0, -7):
+        _chk(rc, "ref_fast_detect_after")
+    return pts[:cnt.value].copy(), rc == 0
+
+
 def scale_bilinear(which, img, out_w, out_h, width=None):
     """CompVImage::scale(..., COMPV_INTERPOLATION_TYPE_BILINEAR): 8-bit fixed-point bilinear kernel."""
     w, h, stride = _frame_args(img, width)

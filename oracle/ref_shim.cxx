@@ -261,6 +261,25 @@ int ref_orb_detect(const uint8_t* img, size_t w, size_t h, size_t stride, int fa
 	return 0;
 }
 
+// Reference defect probe: ONE CompVCornerDeteFAST object run on image A and then on image B (what CompVCornerDeteORB does across pyramid levels, orb_dete.cxx:239-246).
+// The detector keeps its strengths / NMS maps while the image STRIDE does not change (fast_dete.cxx:186-197) and only rewrites the positions of the new, smaller image,
+// so B's result can contain corners left over from A.  Returns B's point count through *count (and the points).
+int ref_fast_detect_after(const uint8_t* imgA, size_t wA, size_t hA, const uint8_t* imgB, size_t wB, size_t hB, void* pts, size_t capacity, size_t* count)
+{
+	CompVMatPtr a, b;
+	SHIM_CHECK(CompVImage::wrap(COMPV_SUBTYPE_PIXELS_Y, imgA, wA, hA, wA, &a));
+	SHIM_CHECK(CompVImage::wrap(COMPV_SUBTYPE_PIXELS_Y, imgB, wB, hB, wB, &b));
+	CompVCornerDetePtr dete;
+	SHIM_CHECK(CompVCornerDete::newObj(&dete, COMPV_FAST_ID));
+	SHIM_CHECK(dete->setInt(COMPV_FAST_SET_INT_MAX_FEATURES, -1));
+	CompVInterestPointVector points;
+	SHIM_CHECK(dete->process(a, points));
+	SHIM_CHECK(dete->process(b, points));
+	*count = points.size();
+	if (pts && capacity) memcpy(pts, points.data(), (points.size() < capacity ? points.size() : capacity) * sizeof(CompVInterestPoint));
+	return (a->stride() == b->stride()) ? 0 : -7; // -7: the two images did not share a stride, the maps were re-allocated, nothing to see
+}
+
 // CompVImage::scale, bilinear (base/image/compv_image.cxx:840-905, base/image/compv_image_scale_bilinear.cxx)
 int ref_scale_bilinear(const uint8_t* img, size_t w, size_t h, size_t stride, uint8_t* out, size_t outW, size_t outH)
 {
