@@ -29,6 +29,8 @@ struct cvb200_edge_dete {
 	bool gmaxLanes;
 	bool genericKernel;     // CVB200_EDGE_SET_BOOL_GENERIC_KERNEL: force the generic front kernel (tests)
 	int hystRounds = 8;     // list-driven hysteresis rounds issued per call after round 0 (raised when a call did not converge)
+	// pipeline.cu: the finalize pass also writes the KHT linking bitmap (kht_prepare_bits) and the per-frame edge counts, saving the KHT stage a pass over the edge map
+	unsigned int* khtBits = nullptr; unsigned int* khtEdgeCount = nullptr; int khtWW = 0;
 	int stages = 0; unsigned int* externalGmax = nullptr; // row-strip mode: set around one call by cvb200_edge_dete_process_stages_dev
 	cudaStream_t pendStream = nullptr; bool pendCheck = false; // what edge_enqueue left for edge_finish
 	std::mutex mutex;

@@ -412,6 +412,43 @@ __global__ void canny_finalize_kernel(uint8_t* cls, int W, int H, size_t stride,
 	}
 }
 
+// The same pass that also emits the KHT linking bitmap (1 bit per pixel, bit 31 = leftmost column of a word, two zero rows / one zero word of padding: kht_walk.cuh)
+// and counts the edge pixels of each frame.  32 pixels per thread.
+__global__ void __launch_bounds__(128) canny_finalize_bits_kernel(uint8_t* cls, int W, int H, size_t stride, size_t framePitch, unsigned int* __restrict__ bits, int WW, int padRows,
+	unsigned int* __restrict__ edgeCount)
+{
+	const int y = blockIdx.y, frame = blockIdx.z;
+	uint8_t* row = cls + frame * framePitch + static_cast<size_t>(y) * stride;
+	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+	const int x = wi * 32;
+	unsigned int word = 0;
+	if (x < W) {
+		auto fix = [](unsigned int w) { const unsigned int keep = (w & 0x01010101u) * 0xffu; return w & keep; };
+		auto nz4 = [](unsigned int w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }; // after fix() a byte is 0x00 or 0xff: bit 0 of each byte -> 4 bits
+		if (x + 32 <= W && ((reinterpret_cast<uintptr_t>(row + x) & 15) == 0)) {
+			uint4 a = *reinterpret_cast<const uint4*>(row + x), b = *reinterpret_cast<const uint4*>(row + x + 16);
+			const unsigned int anyA = ((a.x ^ (a.x << 7)) | (a.y ^ (a.y << 7)) | (a.z ^ (a.z << 7)) | (a.w ^ (a.w << 7))) & 0x80808080u;
+			const unsigned int anyB = ((b.x ^ (b.x << 7)) | (b.y ^ (b.y << 7)) | (b.z ^ (b.z << 7)) | (b.w ^ (b.w << 7))) & 0x80808080u;
+			a.x = fix(a.x); a.y = fix(a.y); a.z = fix(a.z); a.w = fix(a.w);
+			b.x = fix(b.x); b.y = fix(b.y); b.z = fix(b.z); b.w = fix(b.w);
+			if (anyA) *reinterpret_cast<uint4*>(row + x) = a;
+			if (anyB) *reinterpret_cast<uint4*>(row + x + 16) = b;
+			word = (nz4(a.x) & 15u) | ((nz4(a.y) & 15u) << 4) | ((nz4(a.z) & 15u) << 8) | ((nz4(a.w) & 15u) << 12)
+				| ((nz4(b.x) & 15u) << 16) | ((nz4(b.y) & 15u) << 20) | ((nz4(b.z) & 15u) << 24) | ((nz4(b.w) & 15u) << 28);
+		}
+		else {
+			for (int k = 0; k < 32 && x + k < W; ++k) {
+				if (row[x + k] == CLS_WEAK) row[x + k] = 0;
+				if (row[x + k]) word |= 1u << k;
+			}
+		}
+		bits[(static_cast<size_t>(frame) * (H + 2 * padRows) + y + padRows) * WW + wi + 1] = __brev(word);
+	}
+	unsigned int c = __popc(word);
+	for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&edgeCount[frame], c);
+}
+
 // sum of a u8 frame (CompVMathUtils::sum<uint8_t,uint32_t>, canny_dete.cxx:243) -> PERCENT_OF_MEAN thresholds (:253-258)
 __global__ void frame_sum_kernel(const uint8_t* in, int W, int H, size_t stride, size_t framePitch, unsigned int* sums)
 {
@@ -727,7 +764,12 @@ int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, s
 
 	dim3 fg(static_cast<unsigned>(div_up(div_up(width, 16), 128)), static_cast<unsigned>(height), static_cast<unsigned>(batch));
 	CVB_REQUIRE(fg.y <= 65535, CVB200_E_OUT_OF_BOUND);
-	{
+	if (d->khtBits) {
+		dim3 bg(static_cast<unsigned>(div_up(div_up(width, 32), 128)), static_cast<unsigned>(height), static_cast<unsigned>(batch));
+		KernelScope ks_("canny_finalize", stream);
+		canny_finalize_bits_kernel<<<bg, 128, 0, stream>>>(edges, p.W, p.H, stride, framePitch, d->khtBits, d->khtWW, 2, d->khtEdgeCount);
+	}
+	else {
 		KernelScope ks_("canny_finalize", stream);
 		canny_finalize_kernel<<<fg, 128, 0, stream>>>(edges, p.W, p.H, stride, framePitch);
 	}

@@ -623,10 +623,11 @@ kht_peaks_emit_kernel(const int* __restrict__ accAll, const unsigned int* __rest
 // ---- std::sort's permutation + the sweep, one CTA per frame ----
 #define KSORT_THREADS 256
 #define KSORT_WARPS (KSORT_THREADS / 32)
-#define KSORT_SMEM_ITEMS 6144 // up to this many cells the whole sort runs in shared memory: 6144 * (8 + 4 + 4) bytes = 96 KB
+#define KSORT_SMEM_ITEMS 8192 // up to this many cells the whole sort runs in shared memory: 8192 * (8 + 2 + 2) bytes = 96 KB (16-bit position lists)
 
 // one partition step of a[first, last) by one warp: the closed form of std_sort_emu.cuh (sse_partition_closed_form) with ballots for the two ordered compactions
-__device__ int ksort_warp_partition(sse_item* a, int first, int last, unsigned int* Ls, unsigned int* Rs)
+template <typename IDX>
+__device__ int ksort_warp_partition(sse_item* a, int first, int last, IDX* Ls, IDX* Rs)
 {
 	const int lane = threadIdx.x & 31;
 	const unsigned int lt = (1u << lane) - 1u;
@@ -638,14 +639,14 @@ __device__ int ksort_warp_partition(sse_item* a, int first, int last, unsigned i
 		const int i = base + lane;
 		const bool flag = i < last && !(sse_key(a[i]) > pk);
 		const unsigned int bal = __ballot_sync(0xffffffffu, flag);
-		if (flag) Ls[first + nL + __popc(bal & lt)] = static_cast<unsigned int>(i);
+		if (flag) Ls[first + nL + __popc(bal & lt)] = static_cast<IDX>(i);
 		nL += __popc(bal);
 	}
 	for (int base = last - 1; base > first; base -= 32) {
 		const int i = base - lane;
 		const bool flag = i > first && !(pk > sse_key(a[i]));
 		const unsigned int bal = __ballot_sync(0xffffffffu, flag);
-		if (flag) Rs[first + nR + __popc(bal & lt)] = static_cast<unsigned int>(i);
+		if (flag) Rs[first + nR + __popc(bal & lt)] = static_cast<IDX>(i);
 		nR += __popc(bal);
 	}
 	__syncwarp();
@@ -653,14 +654,14 @@ __device__ int ksort_warp_partition(sse_item* a, int first, int last, unsigned i
 	int K = 0;
 	for (int base = 0; base < m; base += 32) { // L ascends and R descends: the predicate is monotone, stop at the first chunk that contains a false
 		const int k = base + lane;
-		const bool ok = k < m && Ls[first + k] < Rs[first + k];
+		const bool ok = k < m && static_cast<unsigned int>(Ls[first + k]) < static_cast<unsigned int>(Rs[first + k]);
 		const unsigned int bal = __ballot_sync(0xffffffffu, ok);
 		K += __popc(bal);
 		if (bal != 0xffffffffu) break;
 	}
 	for (int k = lane; k < K; k += 32) { const unsigned int i = Ls[first + k], j = Rs[first + k]; const sse_item t = a[i]; a[i] = a[j]; a[j] = t; }
-	const unsigned int cl = (K < nL) ? Ls[first + K] : 0xffffffffu;
-	const unsigned int cr = (K > 0) ? Rs[first + K - 1] : static_cast<unsigned int>(last);
+	const unsigned int cl = (K < nL) ? static_cast<unsigned int>(Ls[first + K]) : 0xffffffffu;
+	const unsigned int cr = (K > 0) ? static_cast<unsigned int>(Rs[first + K - 1]) : static_cast<unsigned int>(last);
 	__syncwarp();
 	return static_cast<int>(cl < cr ? cl : cr);
 }
@@ -679,8 +680,9 @@ kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict
 	const int nv = static_cast<int>(fr.nVotes);
 	if (nv == 0) { if (tid == 0) counts[frame] = 0; return; }
 	const KhtVote* votes = votesAll + fr.voteOff;
-	sse_item* a; unsigned int* Ls; unsigned int* Rs;
-	if (nv <= KSORT_SMEM_ITEMS) { a = reinterpret_cast<sse_item*>(ksortSmem); Ls = reinterpret_cast<unsigned int*>(a + KSORT_SMEM_ITEMS); Rs = Ls + KSORT_SMEM_ITEMS; }
+	const bool inSmem = nv <= KSORT_SMEM_ITEMS;       // block-uniform
+	sse_item* a; unsigned int* Ls = nullptr; unsigned int* Rs = nullptr; unsigned short* Ls16 = nullptr; unsigned short* Rs16 = nullptr;
+	if (inSmem) { a = reinterpret_cast<sse_item*>(ksortSmem); Ls16 = reinterpret_cast<unsigned short*>(a + KSORT_SMEM_ITEMS); Rs16 = Ls16 + KSORT_SMEM_ITEMS; }
 	else { a = itemsAll + fr.voteOff; Ls = listsAll + 2 * fr.voteOff; Rs = Ls + nv; }
 	for (int i = tid; i < nv; i += KSORT_THREADS) a[i] = (static_cast<sse_item>(static_cast<unsigned int>(votes[i].count)) << 32) | static_cast<unsigned int>(i);
 	__syncthreads();
@@ -698,7 +700,7 @@ kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict
 			for (int r = warp; r < cnt; r += KSORT_WARPS) {
 				const int f = lvl[cur][3 * r], l = lvl[cur][3 * r + 1], d = lvl[cur][3 * r + 2];
 				if (d == 0) { if (lane == 0) sse_heap_sort(a + f, l - f); __syncwarp(); continue; } // the depth-limit fallback of introsort
-				const int cut = ksort_warp_partition(a, f, l, Ls, Rs);
+				const int cut = inSmem ? ksort_warp_partition<unsigned short>(a, f, l, Ls16, Rs16) : ksort_warp_partition<unsigned int>(a, f, l, Ls, Rs);
 				if (lane < 2) {
 					const int cf = lane ? cut : f, cl = lane ? l : cut;
 					if (cl - cf > SSE_THRESHOLD) { const int k = atomicAdd(&sCnt[cur ^ 1], 1); lvl[cur ^ 1][3 * k] = cf; lvl[cur ^ 1][3 * k + 1] = cl; lvl[cur ^ 1][3 * k + 2] = d - 1; }
@@ -837,16 +839,20 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	KhtFrame* dFrames = h->frames.as<KhtFrame>();
 	const unsigned int B = static_cast<unsigned int>(batch);
 
-	CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream)); // the zero border rows / words the walker relies on
-	CVB_CUDA(cudaMemsetAsync(dEdgeCount, 0, ((batch * 4 + 15) & ~static_cast<size_t>(15)) + sizeof(KhtMeta), stream));
+	const bool bitsReady = h->bitsPrepared; // the producer of the edge map (canny_finalize in the pipeline) has already written the bitmap and the edge counts
+	h->bitsPrepared = false;
+	if (!bitsReady) {
+		CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream)); // the zero border rows / words the walker relies on
+		CVB_CUDA(cudaMemsetAsync(dEdgeCount, 0, ((batch * 4 + 15) & ~static_cast<size_t>(15)) + sizeof(KhtMeta), stream));
+	}
 	CVB_CUDA(cudaMemsetAsync(h->acc.p, 0, batch * accCells * 4, stream));
-	{
+	if (!bitsReady) {
 		dim3 grid(static_cast<unsigned>(div_up(g.WW, 64)), static_cast<unsigned>(g.H), B);
 		CVB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, CVB200_E_OUT_OF_BOUND);
 		KernelScope ks_("kht_bits", stream);
 		kht_bits_kernel<<<grid, 64, 0, stream>>>(edges, h->bits.as<unsigned int>(), g, dEdgeCount);
+		CVB_LAUNCHED();
 	}
-	CVB_LAUNCHED();
 	{ KernelScope ks_("kht_offsets", stream);
 	  kht_offsets1_kernel<<<1, 256, 0, stream>>>(dEdgeCount, dFrames, dMeta, static_cast<int>(batch), g.minSize, h->posCapEl, h->strCapEl); }
 	CVB_LAUNCHED();
@@ -890,7 +896,7 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	CVB_LAUNCHED();
 	{
 		static std::atomic<unsigned int> attrSet{0};
-		const int smem = KSORT_SMEM_ITEMS * (8 + 4 + 4);
+		const int smem = KSORT_SMEM_ITEMS * (8 + 2 + 2);
 		CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(kht_peaks_sort_kernel), smem, attrSet));
 		const unsigned int lim = (h->maxLines <= 0) ? static_cast<unsigned int>(INT_MAX) : static_cast<unsigned int>(h->maxLines);
 		KernelScope ks_("kht_peaks_sort", stream);
@@ -904,6 +910,23 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	CVB_CUDA(cudaMemcpyAsync(hMeta + sizeof(KhtMeta), dFrames + (batch - 1), sizeof(KhtFrame), cudaMemcpyDeviceToHost, stream));
 	CVB_CUDA(cudaMemcpyAsync(h->hCounts.p, h->dCounts.p, batch * 8, cudaMemcpyDeviceToHost, stream));
 	h->pendBatch = batch; h->pendCapacity = capacity; h->pendStream = stream;
+	return CVB200_S_OK;
+}
+
+// For a producer that can write the linking bitmap itself (pipeline.cu: canny_finalize): sizes and zeroes the bitmap and the edge counters of the NEXT kht_enqueue on
+// this object and hands out where they are.  Bitmap layout: (H + 2*KHT_PADR) rows of WW = ceil(W/32) + 2 words per frame, image row y at row y + KHT_PADR, pixel x in
+// word 1 + x/32 at bit 31 - x%32 (kht_walk.cuh).
+int cvb::kht_prepare_bits(cvb200_hough* h, size_t width, size_t height, size_t batch, cudaStream_t stream, unsigned int** bits, unsigned int** edgeCount, int* wordsPerRow)
+{
+	const size_t WW = div_up(width, 32) + 2;
+	const size_t bitWords = (height + 2 * KHT_PADR) * WW;
+	const size_t countBytes = ((batch * 4 + 15) & ~static_cast<size_t>(15)) + sizeof(KhtMeta);
+	CVB_CHECK(h->bits.ensure(batch * bitWords * 4));
+	CVB_CHECK(h->edgeCount.ensure(countBytes));
+	CVB_CUDA(cudaMemsetAsync(h->bits.p, 0, batch * bitWords * 4, stream));
+	CVB_CUDA(cudaMemsetAsync(h->edgeCount.p, 0, countBytes, stream));
+	*bits = h->bits.as<unsigned int>(); *edgeCount = h->edgeCount.as<unsigned int>(); *wordsPerRow = static_cast<int>(WW);
+	h->bitsPrepared = true;
 	return CVB200_S_OK;
 }
 

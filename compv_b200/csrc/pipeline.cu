@@ -90,7 +90,11 @@ int slot_enqueue(PipeState& st, PipeSlot& s, const Job& j, size_t f0, size_t nf)
 	CVB_CHECK(s.edges.ensure(j.sub * j.frameBytes));
 	const int slotId = static_cast<int>(f0 / j.sub);
 	trace_mark(s.stream, "canny>", slotId);
-	CVB_CHECK(edge_enqueue(&s.canny, s.dIn, j.width, j.height, j.stride, s.edges.as<uint8_t>(), nf, s.inPitch, s.stream));
+	// the Canny finalize pass writes the linking bitmap and the edge counts of this sub-batch straight into the KHT object's buffers
+	CVB_CHECK(kht_prepare_bits(&s.hough, j.width, j.height, nf, s.stream, &s.canny.khtBits, &s.canny.khtEdgeCount, &s.canny.khtWW));
+	const int rcEdge = edge_enqueue(&s.canny, s.dIn, j.width, j.height, j.stride, s.edges.as<uint8_t>(), nf, s.inPitch, s.stream);
+	s.canny.khtBits = nullptr; s.canny.khtEdgeCount = nullptr;
+	if (rcEdge != CVB200_S_OK) { s.hough.bitsPrepared = false; return rcEdge; }
 	trace_mark(s.stream, "canny<", slotId);
 	s.hough.traceSlot = slotId;
 	CVB_CHECK(kht_enqueue(&s.hough, s.edges.as<uint8_t>(), j.width, j.height, j.stride, nf, j.frameBytes, j.capacity, s.stream));
