@@ -843,13 +843,21 @@ int cvb200_edge_dete_process(cvb200_edge_dete_t* d, const uint8_t* image, size_t
 	CVB_REQUIRE_INIT();
 	CVB_REQUIRE(d && image && edges && width && height && stride >= width, CVB200_E_INVALID_PARAMETER);
 	const size_t n = stride * height;
-	{
-		std::lock_guard<std::mutex> lock(d->mutex);
-		CVB_CHECK(d->hostIn.ensure(n));
-		CVB_CHECK(d->hostOut.ensure(n));
+	// the object's staging buffers are used for the whole call: one caller at a time per object (the reference's detector objects are not thread-safe either)
+	std::lock_guard<std::mutex> lock(d->mutex);
+	CVB_CHECK(d->hostIn.ensure(n));
+	CVB_CHECK(d->hostOut.ensure(n));
+	// row by row: the caller's last row need not be padded to the stride
+	CVB_CUDA(cudaMemcpy2DAsync(d->hostIn.p, stride, image, stride, width, height, cudaMemcpyHostToDevice, 0));
+	int rc = CVB200_S_OK;
+	for (int attempt = 0; attempt < 12; ++attempt) {
+		rc = edge_enqueue(d, d->hostIn.as<uint8_t>(), width, height, stride, d->hostOut.as<uint8_t>(), 1, 0, nullptr);
+		bool again = false;
+		if (rc == CVB200_S_OK) rc = edge_finish(d, &again);
+		if (rc != CVB200_S_OK || !again) break;
+		if (attempt == 11) rc = CVB200_E_INVALID_STATE;
 	}
-	CVB_CUDA(cudaMemcpyAsync(d->hostIn.p, image, n, cudaMemcpyHostToDevice, 0));
-	CVB_CHECK(cvb200_edge_dete_process_dev(d, d->hostIn.as<uint8_t>(), width, height, stride, d->hostOut.as<uint8_t>(), 1, 0, nullptr));
+	if (rc != CVB200_S_OK) { cudaStreamSynchronize(0); return rc; }
 	CVB_CUDA(cudaMemcpy2DAsync(edges, stride, d->hostOut.p, stride, width, height, cudaMemcpyDeviceToHost, 0));
 	CVB_CUDA(cudaStreamSynchronize(0));
 	return CVB200_S_OK;
