@@ -225,39 +225,68 @@ fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p
 	}
 }
 
-// exclusive prefix of popc(mask word) per frame; one block per frame, 1024 threads
-__global__ void __launch_bounds__(1024)
-fast_rank_prefix_kernel(const unsigned int* mask, unsigned int* prefix, unsigned int wordsPerFrame)
+// Exclusive prefix of popc(mask word) per frame (the raster rank of every corner).  Three small passes over 4096-word chunks -- chunk sums, a scan of the chunk sums per
+// frame, chunk-local scans + offset -- instead of one 1024-thread block walking a whole frame (round 1: 41 % of the FAST time at 3840x2160).
+constexpr int FR_WORDS_PER_THREAD = 16, FR_THREADS = 256, FR_CHUNK = FR_WORDS_PER_THREAD * FR_THREADS;
+
+__device__ __forceinline__ unsigned int fr_block_exclusive(unsigned int v, unsigned int* sWarp, unsigned int* total)
 {
-	__shared__ unsigned int sWarp[32];
-	__shared__ unsigned int sCarry;
-	const unsigned int* m = mask + blockIdx.x * static_cast<size_t>(wordsPerFrame);
-	unsigned int* out = prefix + blockIdx.x * static_cast<size_t>(wordsPerFrame);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0) sCarry = 0;
+	unsigned int inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+	if (lane == 31) sWarp[warp] = inc;
 	__syncthreads();
-	for (unsigned int base = 0; base < wordsPerFrame; base += 1024) {
+	if (threadIdx.x == 0) { unsigned int run = 0; for (int w = 0; w < FR_THREADS / 32; ++w) { const unsigned int t = sWarp[w]; sWarp[w] = run; run += t; } sWarp[FR_THREADS / 32] = run; }
+	__syncthreads();
+	*total = sWarp[FR_THREADS / 32];
+	return sWarp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(FR_THREADS) fast_rank_chunksum_kernel(const unsigned int* __restrict__ mask, unsigned int* __restrict__ chunkSums, unsigned int wordsPerFrame, unsigned int chunksPerFrame)
+{
+	__shared__ unsigned int sWarp[FR_THREADS / 32 + 1];
+	const unsigned int* m = mask + blockIdx.y * static_cast<size_t>(wordsPerFrame);
+	const unsigned int i0 = (blockIdx.x * FR_THREADS + threadIdx.x) * FR_WORDS_PER_THREAD;
+	unsigned int c = 0;
+#pragma unroll
+	for (int k = 0; k < FR_WORDS_PER_THREAD; ++k) if (i0 + k < wordsPerFrame) c += __popc(m[i0 + k]);
+	unsigned int total;
+	fr_block_exclusive(c, sWarp, &total);
+	if (threadIdx.x == 0) chunkSums[blockIdx.y * chunksPerFrame + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(FR_THREADS) fast_rank_chunkscan_kernel(unsigned int* __restrict__ chunkSums, unsigned int chunksPerFrame)
+{
+	__shared__ unsigned int sWarp[FR_THREADS / 32 + 1];
+	unsigned int* cs = chunkSums + blockIdx.x * chunksPerFrame;
+	unsigned int carry = 0;
+	for (unsigned int base = 0; base < chunksPerFrame; base += FR_THREADS) {
 		const unsigned int i = base + threadIdx.x;
-		const unsigned int c = (i < wordsPerFrame) ? __popc(m[i]) : 0;
-		unsigned int incl = c;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-		if (lane == 31) sWarp[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			unsigned int w = sWarp[lane];
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
-			sWarp[lane] = w; // inclusive over warps
-		}
-		__syncthreads();
-		const unsigned int carry = sCarry;
-		const unsigned int warpBase = warp ? sWarp[warp - 1] : 0;
-		if (i < wordsPerFrame) out[i] = carry + warpBase + incl - c;
-		__syncthreads();
-		if (threadIdx.x == 0) sCarry = carry + sWarp[31];
+		const unsigned int v = (i < chunksPerFrame) ? cs[i] : 0u;
+		unsigned int total;
+		const unsigned int ex = fr_block_exclusive(v, sWarp, &total);
+		if (i < chunksPerFrame) cs[i] = carry + ex;
+		carry += total;
 		__syncthreads();
 	}
+}
+
+__global__ void __launch_bounds__(FR_THREADS) fast_rank_apply_kernel(const unsigned int* __restrict__ mask, const unsigned int* __restrict__ chunkOffsets, unsigned int* __restrict__ prefix,
+	unsigned int wordsPerFrame, unsigned int chunksPerFrame)
+{
+	__shared__ unsigned int sWarp[FR_THREADS / 32 + 1];
+	const unsigned int* m = mask + blockIdx.y * static_cast<size_t>(wordsPerFrame);
+	unsigned int* out = prefix + blockIdx.y * static_cast<size_t>(wordsPerFrame);
+	const unsigned int i0 = (blockIdx.x * FR_THREADS + threadIdx.x) * FR_WORDS_PER_THREAD;
+	unsigned int pc[FR_WORDS_PER_THREAD];
+	unsigned int c = 0;
+#pragma unroll
+	for (int k = 0; k < FR_WORDS_PER_THREAD; ++k) { pc[k] = (i0 + k < wordsPerFrame) ? __popc(m[i0 + k]) : 0u; c += pc[k]; }
+	unsigned int total;
+	unsigned int run = chunkOffsets[blockIdx.y * chunksPerFrame + blockIdx.x] + fr_block_exclusive(c, sWarp, &total);
+#pragma unroll
+	for (int k = 0; k < FR_WORDS_PER_THREAD; ++k) { if (i0 + k < wordsPerFrame) out[i0 + k] = run; run += pc[k]; }
 }
 
 // CompVInterestPoint layout (base/include/compv/base/compv_common.h:629-656)
@@ -299,7 +328,7 @@ struct cvb200_corner_dete {
 	int orbMaxFeatures = 2000;
 	cvb200_corner_dete* orbFast = nullptr;
 	DevBuf orbLevel, orbPts, orbMom;
-	DevBuf mask, prefix, list, counters, hostIn, points;
+	DevBuf mask, prefix, list, counters, hostIn, points, rankSums;
 	HostBuf hostCount;
 	std::mutex mutex;
 };
@@ -346,8 +375,13 @@ static int fast_launch(cvb200_corner_dete* d, const uint8_t* image, size_t width
 	CVB_LAUNCHED();
 	if (points) {
 		{
+			const unsigned int chunks = static_cast<unsigned int>(div_up(words, FR_CHUNK));
+			CVB_CHECK(d->rankSums.ensure(batch * chunks * sizeof(unsigned int)));
 			KernelScope ks_("fast_rank_prefix", stream);
-			fast_rank_prefix_kernel<<<static_cast<unsigned>(batch), 1024, 0, stream>>>(p.mask, d->prefix.as<unsigned int>(), words);
+			fast_rank_chunksum_kernel<<<dim3(chunks, static_cast<unsigned>(batch)), FR_THREADS, 0, stream>>>(p.mask, d->rankSums.as<unsigned int>(), words, chunks);
+			fast_rank_chunkscan_kernel<<<static_cast<unsigned>(batch), FR_THREADS, 0, stream>>>(d->rankSums.as<unsigned int>(), chunks);
+			fast_rank_apply_kernel<<<dim3(chunks, static_cast<unsigned>(batch)), FR_THREADS, 0, stream>>>(p.mask, d->rankSums.as<unsigned int>(), d->prefix.as<unsigned int>(), words, chunks);
+			g_launches.fetch_add(2, std::memory_order_relaxed);
 		}
 		CVB_LAUNCHED();
 		{
@@ -525,7 +559,7 @@ int cvb200_corner_dete_free(cvb200_corner_dete_t** dete)
 		cvb200_corner_dete* d = *dete;
 		if (d->orbFast) { cvb200_corner_dete_t* f = d->orbFast; cvb200_corner_dete_free(&f); }
 		d->orbLevel.release(); d->orbPts.release(); d->orbMom.release();
-		d->mask.release(); d->prefix.release(); d->list.release(); d->counters.release(); d->hostIn.release(); d->points.release(); d->hostCount.release();
+		d->mask.release(); d->prefix.release(); d->list.release(); d->counters.release(); d->hostIn.release(); d->points.release(); d->hostCount.release(); d->rankSums.release();
 		delete d;
 		*dete = nullptr;
 	}
