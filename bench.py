@@ -429,12 +429,18 @@ def main():
     # ---- roofline of the dominant kernel: per-kernel CUDA-event timing over extra steps (rank 0) ----
     roof, kernels = None, {}
     if rank == 0:
+        # Per-kernel CUDA events.  The timed region above overlaps sub-batches on several streams, where a kernel's event-to-event time includes waiting for the others;
+        # for the roofline the same steps are run once more with ONE slot (CVB200_PIPE_SLOTS=1: every kernel launched once per step on the whole batch, nothing overlapped).
+        os.environ["CVB200_PIPE_SLOTS"] = "1"
+        for _ in range(2):
+            step_dev()
         cvb.lib().cvb200_profile_begin()
-        psteps = min(args.steps, 10)
+        psteps = min(args.steps, 5)
         for _ in range(psteps):
             step_dev()
         buf = C.create_string_buffer(1 << 16)
         cvb.check(cvb.lib().cvb200_profile_end(buf, C.c_size_t(len(buf))), "cvb200_profile_end")
+        os.environ.pop("CVB200_PIPE_SLOTS", None)
         for ln in buf.value.decode().splitlines():
             name, cnt, ms = ln.split()
             kernels[name] = {"launches": int(cnt), "total_ms": float(ms), "avg_ms": float(ms) / max(int(cnt), 1)}
@@ -443,24 +449,27 @@ def main():
         for k in kernels.values():
             k["share"] = k["total_ms"] / psteps / step_ms
         peak, how = load_peaks()
-        # the dominant kernel by device time; every launch of it processes the whole batch
-        alg_bytes = ALG_BYTES_PER_PX.get(top, 1.0) * B * W * H
+        # the dominant kernel by device time; in this serial pass every launch of it processes the whole batch
+        frames_per_launch = B * psteps / max(kernels[top]["launches"], 1)
+        alg_bytes = ALG_BYTES_PER_PX.get(top, 1.0) * frames_per_launch * W * H
         achieved = alg_bytes / (kernels[top]["avg_ms"] * 1e-3) / 1e9
         traffic, traffic_src = None, None
-        try:  # dram bytes read + written by that kernel in one `ncu --set full` capture of this command (profiles/), scaled to this launch's frame count
-            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
-            if top in tj["bytes_per_launch"]:
-                traffic = tj["bytes_per_launch"][top] * B / tj["frames_per_launch"]
+        try:  # dram bytes read + written by that kernel in one `ncu --set full` capture (profiles/), per frame, scaled to this launch's frame count
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+            if top in tj["bytes_per_frame"]:
+                traffic = tj["bytes_per_frame"][top] * frames_per_launch
                 traffic_src = tj["source"]
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": how, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": kernels[top]["avg_ms"],
-                "note": ("kht_link is the order-dependent linking walk (one warp per frame): latency-bound by construction, see DESIGN.md. " if top == "kht_link" else "")
-                + "Sub-batches run concurrently on several streams: per-kernel times overlap, `share` is of the SUMMED kernel time, not of the step."}
+                "frames_per_launch": frames_per_launch, "serial_step_ms": step_ms,
+                "note": ("kht_link is the order-dependent linking walk (one warp per frame): bound by the issue latency of its dependent instruction chain, not by HBM, see DESIGN.md section 5. " if top == "kht_link" else "")
+                + "Measured in a serial pass (one pipeline slot, no overlap) after the timed region; `kernels[*].share` is the share of that serial step."}
         if "canny_front" in kernels and top != "canny_front":
-            cf = ALG_BYTES_PER_PX["canny_front"] * B * W * H / (kernels["canny_front"]["avg_ms"] * 1e-3) / 1e9
-            roof["canny_front"] = {"achieved": cf, "frac": cf / peak, "avg_launch_ms": kernels["canny_front"]["avg_ms"]}
+            fpl = B * psteps / max(kernels["canny_front"]["launches"], 1)
+            cf = ALG_BYTES_PER_PX["canny_front"] * fpl * W * H / (kernels["canny_front"]["avg_ms"] * 1e-3) / 1e9
+            roof["canny_front"] = {"achieved": cf, "frac": cf / peak, "avg_launch_ms": kernels["canny_front"]["avg_ms"], "frames_per_launch": fpl}
 
     # ---- CPU baseline: the compiled reference on this host's cores (rank 0, N=1 only) ----
     cpu = None
