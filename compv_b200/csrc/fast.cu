@@ -30,7 +30,8 @@ constexpr int FA_INW = 36;                 // words per staged row (144-byte TMA
 constexpr int FA_IN_ROWS = FA_TH + 8;      // image rows y0-4 .. y0+TH+3
 constexpr int FA_S_ROWS = FA_TH + 2;       // strength rows y0-1 .. y0+TH
 constexpr int FA_S_PITCH = 128;            // strength tile: one byte per staged column
-constexpr int FA_QCAP = FA_S_ROWS * 122;   // every pixel of the strength region may be a candidate
+constexpr int FA_QWARP = 8 * 128;          // candidate queue of one warp: every pixel of its (at most 8) rows may be a candidate
+constexpr int FA_QCAP = FA_QWARP * FA_WARPS;
 
 struct FastKParams {
 	const uint8_t* in;
@@ -45,9 +46,13 @@ struct FastKParams {
 	unsigned int maskWordsPerFrame, listCap;
 };
 
-// circle offsets (dx, dy) in the reference's order (fast_dete.cxx:221-238)
-__constant__ int c_circle_dx[16] = { 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1 };
-__constant__ int c_circle_dy[16] = { -3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3 };
+// circle offsets (dx, dy) in the reference's order (fast_dete.cxx:221-238); compile-time so that an unrolled loop turns them into immediate load offsets
+__host__ __device__ constexpr int circle_dx(int k) { return (k <= 3) ? k : (k <= 5) ? 3 : (k <= 8) ? (8 - k) : (k <= 11) ? (8 - k) : (k <= 13) ? -3 : (k - 16); }
+__host__ __device__ constexpr int circle_dy(int k) { return circle_dx((k + 12) & 15); }
+static_assert(circle_dx(0) == 0 && circle_dx(1) == 1 && circle_dx(2) == 2 && circle_dx(3) == 3 && circle_dx(4) == 3 && circle_dx(5) == 3 && circle_dx(6) == 2 && circle_dx(7) == 1
+	&& circle_dx(8) == 0 && circle_dx(9) == -1 && circle_dx(10) == -2 && circle_dx(11) == -3 && circle_dx(12) == -3 && circle_dx(13) == -3 && circle_dx(14) == -2 && circle_dx(15) == -1, "circle dx");
+static_assert(circle_dy(0) == -3 && circle_dy(1) == -3 && circle_dy(2) == -2 && circle_dy(3) == -1 && circle_dy(4) == 0 && circle_dy(5) == 1 && circle_dy(6) == 2 && circle_dy(7) == 3
+	&& circle_dy(8) == 3 && circle_dy(9) == 3 && circle_dy(10) == 2 && circle_dy(11) == 1 && circle_dy(12) == 0 && circle_dy(13) == -1 && circle_dy(14) == -2 && circle_dy(15) == -3, "circle dy");
 
 // bit i of the result is set when bits i..i+n-1 (circularly, 16 positions) of m are all set
 __device__ __forceinline__ unsigned int arc_starts(unsigned int m, int n)
@@ -60,7 +65,7 @@ __device__ __forceinline__ unsigned int arc_starts(unsigned int m, int n)
 	return d & 0xffffu;
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 3)
+__global__ void __launch_bounds__(FA_THREADS, 5)
 fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -69,7 +74,6 @@ fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p
 	uint8_t* sS = reinterpret_cast<uint8_t*>(sIn + FA_IN_ROWS * FA_INW + 4);            // FA_S_ROWS x 128 bytes, +1 row of slack on each side
 	unsigned short* sQ = reinterpret_cast<unsigned short*>(sS + (FA_S_ROWS + 2) * FA_S_PITCH); // candidate queue
 	uint64_t* bar = reinterpret_cast<uint64_t*>(sQ + ((FA_QCAP + 3) & ~3));
-	__shared__ unsigned int sQn;
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int W = p.W, H = p.H;
@@ -81,7 +85,6 @@ fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p
 	const int woff = ((x0 - 4) - xTma) >> 2;
 	const int t = p.threshold;
 
-	if (threadIdx.x == 0) sQn = 0;
 	if (p.useTma) {
 		if (threadIdx.x == 0) {
 			mbar_init(bar, 1);
@@ -112,61 +115,70 @@ fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p
 	if (p.useTma) mbar_wait(bar, 0);
 	uint8_t* sStr = sS + FA_S_PITCH; // row 0 of the strength region (image y0-1); one slack row above and below
 
-	// ---- stage A: compass test, 4 px per lane, rows of the strength region ----
-	const int need = (p.N == 12) ? 3 : 2;
-	for (int rs = warp; rs < FA_S_ROWS; rs += FA_WARPS) {
-		const int y = y0 - 1 + rs;
-		unsigned int cand = 0; // 4 bits
-		if (y >= 3 && y < H - 3) {
-			const unsigned int* q = &sIn[(rs + 3) * FA_INW + woff + lane]; // staged row of image y (yIn0 = y0-4 -> row index y - yIn0 = rs + 3)
+	// ---- stage A: compass filter, 4 px per lane, rows of the strength region; stage B: full segment test on the survivors ----
+	// A corner has at least `need` of its 4 compass pixels darker than pc - t, or as many brighter than pc + t (a contiguous arc of N of the 16 circle pixels always
+	// holds 2 (N = 9) / 3 (N = 12) of them).  The filter keeps the weaker condition "|c - pc| > t for at least `need` compass pixels", which byte-wise SIMD evaluates
+	// for the lane's four pixels at once (one absolute-difference instruction per compass word, the comparison with t through the carry into bit 7 of each byte);
+	// the segment test of stage B is exact whatever the filter lets through.  Survivors go to a queue private to the warp (its rows interleave with the other
+	// warps', so the queues balance).
+	const bool need3 = (p.N == 12), tBig = (t >= 128);
+	const unsigned int K = static_cast<unsigned int>((tBig ? 0xff : 0x7f) - t) * 0x01010101u;
+	unsigned int xOk = 0; // which of the lane's 4 columns may hold a corner of this tile's strength region
+#pragma unroll
+	for (int i = 0; i < 4; ++i) { const int x = xl + i; if (x >= 3 && x < W - 3 && x >= x0 - 1 && x <= x0 + FA_TW) xOk |= 1u << i; }
+	unsigned short* myQ = sQ + warp * FA_QWARP;
+	const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn) + woff * 4; // byte (r, c): column c <-> image x0-4+c
+	// A warp owns rows warp, warp + 8, ... of the strength region: at most 8 rows x 4 px per lane = one 32-bit candidate mask per lane, no queue traffic inside the row loop.
+	static_assert((FA_S_ROWS + FA_WARPS - 1) / FA_WARPS <= 8, "candidate mask: 8 rows x 4 px per lane");
+	unsigned int candAll = 0;
+	{
+		const unsigned int* q = &sIn[(warp + 3) * FA_INW + woff + lane]; // staged row of image y (yIn0 = y0-4 -> row index y - yIn0 = rs + 3)
+		int sh = 0;
+		for (int rs = warp; rs < FA_S_ROWS; rs += FA_WARPS, q += FA_WARPS * FA_INW, sh += 4) {
+			const int y = y0 - 1 + rs;
+			if (y < 3 || y >= H - 3) continue;
 			const unsigned int wc = q[0], wl = q[-1], wr = q[1];
 			const unsigned int wu = q[-3 * FA_INW], wd = q[3 * FA_INW];
-			// pixel i: left = byte (i-3) of [wl wc], right = byte (i+3) of [wc wr]
 			const unsigned int wL = __byte_perm(wl, wc, 0x4321);   // bytes x-3..x   -> [wl.b1 wl.b2 wl.b3 wc.b0]
 			const unsigned int wR = __byte_perm(wc, wr, 0x6543);   // bytes x+3..x+6 -> [wc.b3 wr.b0 wr.b1 wr.b2]
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				const int x = xl + i;
-				const int pc = (wc >> (8 * i)) & 0xff;
-				const int br = min(pc + t, 255), dk = max(pc - t, 0);
-				const int cU = (wu >> (8 * i)) & 0xff, cD = (wd >> (8 * i)) & 0xff, cL = (wL >> (8 * i)) & 0xff, cR = (wR >> (8 * i)) & 0xff;
-				const int nd = (cU < dk) + (cD < dk) + (cL < dk) + (cR < dk);
-				const int nb = (cU > br) + (cD > br) + (cL > br) + (cR > br);
-				if ((nd >= need || nb >= need) && x >= 3 && x < W - 3 && x >= x0 - 1 && x <= x0 + FA_TW) cand |= 1u << i;
-			}
-		}
-		// warp-ballot compaction into the queue (order inside the queue is irrelevant)
-		const unsigned int any = __ballot_sync(0xffffffffu, cand != 0);
-		if (any) {
-			const int cnt = __popc(cand);
-			int incl = cnt;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-			const int total = __shfl_sync(0xffffffffu, incl, 31);
-			unsigned int base = 0;
-			if (lane == 0) base = atomicAdd(&sQn, static_cast<unsigned int>(total));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			unsigned int pos = base + incl - cnt;
-#pragma unroll
-			for (int i = 0; i < 4; ++i) if (cand & (1u << i)) sQ[pos++] = static_cast<unsigned short>(rs * FA_S_PITCH + lane * 4 + i);
+			const unsigned int dU = __vabsdiffu4(wu, wc), dD = __vabsdiffu4(wd, wc), dL = __vabsdiffu4(wL, wc), dR = __vabsdiffu4(wR, wc);
+			// bit 7 of every byte: d > t.  (d & 0x7f) + K carries into bit 7 exactly when the low seven bits exceed t (t < 128: OR with d's own bit 7) or t - 128 (AND with it)
+			const unsigned int sU = (dU & 0x7f7f7f7fu) + K, sD = (dD & 0x7f7f7f7fu) + K, sL = (dL & 0x7f7f7f7fu) + K, sR = (dR & 0x7f7f7f7fu) + K;
+			const unsigned int h0 = tBig ? (dU & sU) : (dU | sU), h1 = tBig ? (dD & sD) : (dD | sD), h2 = tBig ? (dL & sL) : (dL | sL), h3 = tBig ? (dR & sR) : (dR | sR);
+			const unsigned int m3 = (h0 & h1) | (h0 & h2) | (h1 & h2);                                 // at least two of the first three
+			const unsigned int hit = need3 ? ((h0 & h1 & h2) | (m3 & h3)) : (m3 | (h3 & (h0 | h1 | h2)));
+			const unsigned int cand = ((((hit >> 7) & 0x01010101u) * 0x01020408u) >> 24) & xOk;       // bits 7/15/23/31 -> bits 0..3
+			candAll |= cand << sh;
 		}
 	}
-	__syncthreads();
+	// queue positions: exclusive prefix of the lanes' candidate counts
+	const int myCnt = __popc(candAll);
+	int incl = myCnt;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+	const unsigned int qn = static_cast<unsigned int>(__shfl_sync(0xffffffffu, incl, 31));
+	{
+		unsigned int pos = static_cast<unsigned int>(incl - myCnt);
+		while (candAll) {
+			const int bidx = __ffs(candAll) - 1;
+			candAll &= candAll - 1;
+			myQ[pos++] = static_cast<unsigned short>((warp + FA_WARPS * (bidx >> 2)) * FA_S_PITCH + lane * 4 + (bidx & 3));
+		}
+	}
+	__syncwarp();
 
-	// ---- stage B: full segment test on the candidates ----
-	const unsigned int qn = sQn;
-	const uint8_t* sInB = reinterpret_cast<const uint8_t*>(sIn) + woff * 4; // byte (r, c): column c <-> image x0-4+c
-	for (unsigned int qi = threadIdx.x; qi < qn; qi += FA_THREADS) {
-		const int code = sQ[qi];
-		const int rs = code >> 7, c = code & 127;
-		const uint8_t* ctr = sInB + (rs + 3) * (FA_INW * 4) + c;
+	// ---- stage B: full segment test on the warp's own candidates ----
+	for (unsigned int qi = lane; qi < qn; qi += 32) {
+		const int code = myQ[qi];
+		const int rq = code >> 7, c = code & 127;
+		const uint8_t* ctr = sInB + (rq + 3) * (FA_INW * 4) + c;
 		const int pc = ctr[0];
 		const int br = min(pc + t, 255), dk = max(pc - t, 0);
 		unsigned long long vlo = 0, vhi = 0; // the 16 circle bytes, k = 0..7 in vlo, 8..15 in vhi (registers, no local-memory array)
 		unsigned int md = 0, mb = 0;
 #pragma unroll
 		for (int k = 0; k < 16; ++k) {
-			const int vk = ctr[c_circle_dy[k] * (FA_INW * 4) + c_circle_dx[k]];
+			const int vk = ctr[circle_dy(k) * (FA_INW * 4) + circle_dx(k)];
 			if (k < 8) vlo |= static_cast<unsigned long long>(vk) << (8 * k); else vhi |= static_cast<unsigned long long>(vk) << (8 * (k - 8));
 			md |= (vk < dk ? 1u : 0u) << k;
 			mb |= (vk > br ? 1u : 0u) << k;
@@ -189,7 +201,7 @@ fast_detect_kernel(const __grid_constant__ CUtensorMap tmap, const FastKParams p
 			}
 			strength = max(strength, mn);
 		}
-		if (strength) sStr[rs * FA_S_PITCH + c] = static_cast<uint8_t>(strength);
+		if (strength) sStr[rq * FA_S_PITCH + c] = static_cast<uint8_t>(strength);
 	}
 	__syncthreads();
 

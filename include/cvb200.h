@@ -162,6 +162,8 @@ CVB200_API int cvb200_stream_sync(cvb200_stream_t stream);
 CVB200_API int cvb200_set_host_threads(int n);
 /* Test hook (no device needed): out[i] += 1 for i in [0, n) through the host worker pool. */
 CVB200_API int cvb200_selftest_host_pool(size_t n, unsigned int* out);
+/* mismatches[0..1]: the HOG cells pass' division / square-root sequences against IEEE division / square root over all of their integer operands (test hook) */
+CVB200_API int cvb200_selftest_hog_math(unsigned int* mismatches);
 
 /* ================================================================================================
  * a2 -- separable convolution. Replaces CompVMathConvlt::convlt1<In,Kern,Out> / convlt1FixedPoint

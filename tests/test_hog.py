@@ -104,3 +104,24 @@ def test_cuda_hog_4k_descriptor_size_and_errors(cvb):
     with pytest.raises(_ffi.CvbError) as e:
         d.process(np.zeros((8, 8), np.uint8))         # window smaller than a block (hog_std.cxx:203)
     assert e.value.code == _ffi.E_INVALID_PARAMETER
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,stride", [(100, 80, 101), (71, 33, 75), (1031, 64, 1033)])
+@pytest.mark.parametrize("interp", [53, 54, 55])
+def test_cuda_hog_cells_fast_path_unaligned_rows(cvb, w, h, stride, interp):
+    """8x8 cells on an 8-pixel grid take the tiled cells kernel; rows that are not 4-byte aligned go through its byte-wise tile fill."""
+    d = cvb.CompVHOG.newObj(41, (16, 16), (8, 8), (8, 8), 9, 52, True, interp)
+    for img in _frames(w, h, stride):
+        a = d.process(img, width=w)
+        b = oracle.hog("orc", img, (16, 16), (8, 8), (8, 8), 9, 52, True, interp, width=w)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cuda_hog_math_sequences_match_ieee(cvb):
+    """The cells kernel's division / square root sequences equal IEEE division / square root over every operand they can receive."""
+    import ctypes
+    bad = (ctypes.c_uint * 2)()
+    assert cvb.lib().cvb200_selftest_hog_math(bad) == 0
+    assert list(bad) == [0, 0]
