@@ -7,14 +7,14 @@
 //
 // One kernel per batch does the pixel work (HBM traffic: 1 B/px read + 1 bit/px mask + a few bytes per corner):
 //   stage 0  TMA tile load (u8, 144 x (TH+8) box, zero filled outside the image)
-//   stage A  compass test on 4 px per lane: a contiguous arc of N>=9 of the 16 circle pixels always contains at least
-//            2 (N=9) / 3 (N=12) of the 4 compass pixels, so "fewer than that are darker and fewer are brighter" rejects exactly;
-//            survivors are compacted into a shared-memory queue with warp ballots
-//   stage B  full segment test on the queue (one candidate per thread): 16-bit darker/brighter masks, run-of-N test by shift-and,
-//            strength = max over qualifying arcs of the minimum |difference| in the arc; written to a shared strength tile
+//   stage A  compass filter on 4 px per lane: a contiguous arc of N>=9 of the 16 circle pixels always contains at least 2 (N=9) / 3 (N=12) of the 4 compass
+//            pixels, so a corner has that many compass pixels with |c - centre| > t; byte-wise SIMD (VABSDIFF4 + a carry into bit 7) tests the lane's four pixels at once.
+//            Survivors are marked in a per-lane bit mask (8 rows x 4 px) and compacted into a queue private to the warp once, after the warp's rows
+//   stage B  full segment test on the queue (one candidate per lane): 16-bit darker/brighter masks, run-of-N test by shift-and,
+//            strength = max over qualifying arcs of the minimum |difference| in the arc; written to a shared strength tile (exact whatever stage A let through)
 //   stage C  NMS (suppressed when any 8-neighbour is >= own strength, ties kill both) and emission: a bit in the per-frame corner
 //            mask (atomicOr) + (key,strength) appended to an unordered list
-// then   fast_rank_prefix: exclusive scan of the popcounts of the mask words (one block per frame)
+// then   fast_rank_*: exclusive scan of the popcounts of the mask words (chunk sums, scan of the chunk sums, chunk-local scans)
 //        fast_emit_points: every list entry finds its raster rank = prefix[word] + popc(lower bits) and writes its point there.
 #include "common.cuh"
 #include "tma.cuh"
