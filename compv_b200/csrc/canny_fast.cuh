@@ -66,6 +66,50 @@ __device__ __forceinline__ unsigned int pack4(unsigned int a, unsigned int b, un
 	return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
+
+// ---- packed arithmetic (sm_100a): two IEEE fp32 lanes per instruction (FFMA2 / FADD2 / FMUL2: each lane rounds exactly like the scalar instruction, so the
+// reference's fma chain is reproduced bit for bit at half the issue slots), and two 16-bit lanes in plain 32-bit integer adds (all intermediate values are kept non-negative by a bias).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(unsigned int lo, unsigned int hi)
+{
+	f32x2 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+	return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, unsigned int& lo, unsigned int& hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+	f32x2 r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+	return r;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b)
+{
+	f32x2 r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b)
+{
+	f32x2 r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ f32x2 fadd2_rz(f32x2 a, f32x2 b)
+{
+	f32x2 r;
+	asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+// bytes ia of wa and ib of wb as the float pair (wa.byte[ia], wb.byte[ib])
+__device__ __forceinline__ f32x2 u8x2_to_f32x2(unsigned int wa, int ia, unsigned int wb, int ib, f32x2 negMagic)
+{
+	return fadd2(pk2(__byte_perm(wa, 0x4B000000u, 0x7440u | ia), __byte_perm(wb, 0x4B000000u, 0x7440u | ib)), negMagic);
+}
+
 template <int BKS>
 __global__ void __launch_bounds__(CF_THREADS, 3)
 canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams p)
@@ -122,51 +166,52 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 	}
 
 	if (BKS) {
-		// ---- S1: horizontal blur -> sM (same rows as the input tile).  mid(y,x) = 0 outside [RB, W-RB) x [0, H) ----
+		const f32x2 negMagic = pk2(0xCB000000u, 0xCB000000u), magic = pk2(0x4B000000u, 0x4B000000u); // -2^23, 2^23
+		f32x2 kk[BKS ? BKS : 1];
+#pragma unroll
+		for (int k = 0; k < BKS; ++k) kk[k] = pk2(__float_as_uint(p.k[k]), __float_as_uint(p.k[k]));
+		// ---- S1: horizontal blur -> sM (same rows as the input tile).  mid(y,x) = 0 outside [RB, W-RB) x [0, H): rows outside the image are staged as zeros
+		// and blur to zero by themselves.  Two rows per step: the float pair is (row r, row r+1) of one column, so every FFMA2 serves both rows. ----
 		unsigned int colMask = 0;
 #pragma unroll
 		for (int i = 0; i < 4; ++i) if (xl + i >= RB && xl + i < W - RB) colMask |= 0xffu << (8 * i);
-		for (int r = warp; r < G::IN_ROWS; r += CF_WARPS) {
-			const int y = yIn0 + r;
-			unsigned int outw = 0;
-			if (y >= 0 && y < H && colMask) {
-				const unsigned int* q = &sA[r * CF_INW + woff + lane];
-				const unsigned int wl = q[-1], wc = q[0], wr = q[1];
-				float v[4 + 2 * RB];
+		static_assert(G::IN_ROWS % 2 == 0, "rows are blurred in pairs");
+		for (int r = 2 * warp; r < G::IN_ROWS; r += 2 * CF_WARPS) {
+			const unsigned int* q0 = &sA[r * CF_INW + woff + lane];
+			const unsigned int* q1 = q0 + CF_INW;
+			const unsigned int l0 = q0[-1], c0 = q0[0], r0 = q0[1], l1 = q1[-1], c1 = q1[0], r1 = q1[1];
+			f32x2 v[4 + 2 * RB];
 #pragma unroll
-				for (int j = 0; j < RB; ++j) v[j] = u8_to_f32(wl, 4 - RB + j);
+			for (int j = 0; j < RB; ++j) v[j] = u8x2_to_f32x2(l0, 4 - RB + j, l1, 4 - RB + j, negMagic);
 #pragma unroll
-				for (int j = 0; j < 4; ++j) v[RB + j] = u8_to_f32(wc, j);
+			for (int j = 0; j < 4; ++j) v[RB + j] = u8x2_to_f32x2(c0, j, c1, j, negMagic);
 #pragma unroll
-				for (int j = 0; j < RB; ++j) v[RB + 4 + j] = u8_to_f32(wr, j);
-				unsigned int o[4];
+			for (int j = 0; j < RB; ++j) v[RB + 4 + j] = u8x2_to_f32x2(r0, j, r1, j, negMagic);
+			unsigned int oa[4], ob[4];
 #pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					float s = 0.f;
+			for (int i = 0; i < 4; ++i) {
+				f32x2 s = fmul2(v[i], kk[0]); // == fma(v, k, 0)
 #pragma unroll
-					for (int k = 0; k < BKS; ++k) s = __fmaf_rn(v[i + k], p.k[k], s);
-					o[i] = f32_to_u8_bits(s);
-				}
-				outw = pack4(o[0], o[1], o[2], o[3]) & colMask;
+				for (int k = 1; k < BKS; ++k) s = ffma2(v[i + k], kk[k], s);
+				unpk2(fadd2_rz(s, magic), oa[i], ob[i]);
 			}
-			sM[r * CF_ROWW + lane] = outw;
+			sM[r * CF_ROWW + lane] = pack4(oa[0], oa[1], oa[2], oa[3]) & colMask;
+			sM[(r + 1) * CF_ROWW + lane] = pack4(ob[0], ob[1], ob[2], ob[3]) & colMask;
 		}
 		__syncthreads();
 
-		// ---- S2: vertical blur -> sA (blurred rows: image y0-2 .. y0+TH+1).  B(y,x) = 0 outside [RB, H-RB) ----
+		// ---- S2: vertical blur -> sA (blurred rows: image y0-2 .. y0+TH+1).  B(y,x) = 0 outside [RB, H-RB).  The float pairs are columns (0,1) and (2,3) of the lane's word. ----
 		{
 			constexpr int RPW = G::B_ROWS / CF_WARPS; // 8 rows per warp
 			static_assert(G::B_ROWS % CF_WARPS == 0, "B_ROWS must split evenly across warps");
 			const int rb0 = warp * RPW;
-			float win[RPW + 2 * RB][4];
+			f32x2 win[RPW + 2 * RB][2];
 #pragma unroll
 			for (int r = 0; r < RPW + 2 * RB; ++r) {
 				const unsigned int w = sM[(rb0 + r) * CF_ROWW + lane];
-#pragma unroll
-				for (int i = 0; i < 4; ++i) win[r][i] = u8_to_f32(w, i);
+				win[r][0] = u8x2_to_f32x2(w, 0, w, 1, negMagic);
+				win[r][1] = u8x2_to_f32x2(w, 2, w, 3, negMagic);
 			}
-			// all warps must finish READING sM... they read sM and write sA (the dead input tile): but other warps may still read sA in S1?
-			// No: S1 finished for every warp at the barrier above.
 #pragma unroll
 			for (int j = 0; j < RPW; ++j) {
 				const int y = y0 - 2 + rb0 + j;
@@ -174,11 +219,11 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 				if (y >= RB && y < H - RB) {
 					unsigned int o[4];
 #pragma unroll
-					for (int i = 0; i < 4; ++i) {
-						float s = 0.f;
+					for (int h = 0; h < 2; ++h) {
+						f32x2 s = fmul2(win[j][h], kk[0]);
 #pragma unroll
-						for (int k = 0; k < BKS; ++k) s = __fmaf_rn(win[j + k][i], p.k[k], s);
-						o[i] = f32_to_u8_bits(s);
+						for (int k = 1; k < BKS; ++k) s = ffma2(win[j + k][h], kk[k], s);
+						unpk2(fadd2_rz(s, magic), o[2 * h], o[2 * h + 1]);
 					}
 					outw = pack4(o[0], o[1], o[2], o[3]);
 				}
@@ -195,21 +240,28 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 	{
 		constexpr int RPW = (G::G_ROWS + CF_WARPS - 1) / CF_WARPS; // 8
 		const int rg0 = warp * RPW;
-		// per source row: hs[i] = p[i-1] + 2p[i] + p[i+1], hd[i] = p[i+1] - p[i-1]
-		int hs[3][4], hd[3][4];
+		// Two pixels per 32-bit integer instruction: 16-bit halves hold pixels (0, 2) and (1, 3) of the lane's word, every intermediate value is kept non-negative by a bias
+		// (so no borrow crosses the halves).  Per source row: hs = p[i-1] + 2p[i] + p[i+1] (<= 1020), hd = p[i+1] - p[i-1] + 256.
+		unsigned int hs[3][2], hd[3][2];
 		// the gradient source is the blurred tile (pitch 32, word = lane) or, without blur, the staged input itself (pitch 36, word = woff+lane)
 		const int srcPitch = BKS ? CF_ROWW : CF_INW;
 		const unsigned int* src = sA + (BKS ? 0 : woff) + lane;
 		auto loadRow = [&](int rb, int slot) {
 			const unsigned int* sw = src + rb * srcPitch;
 			const unsigned int wl = sw[-1], wc = sw[0], wr = sw[1];
-			int q[6];
-			q[0] = static_cast<int>(wl >> 24);
-			q[1] = static_cast<int>(wc & 0xff); q[2] = static_cast<int>((wc >> 8) & 0xff); q[3] = static_cast<int>((wc >> 16) & 0xff); q[4] = static_cast<int>(wc >> 24);
-			q[5] = static_cast<int>(wr & 0xff);
-#pragma unroll
-			for (int i = 0; i < 4; ++i) { hs[slot][i] = q[i] + 2 * q[i + 1] + q[i + 2]; hd[slot][i] = q[i + 2] - q[i]; }
+			const unsigned int B = __byte_perm(wc, 0u, 0x4240);  // (p0, p2)
+			const unsigned int Cc = __byte_perm(wc, 0u, 0x4341); // (p1, p3)
+			const unsigned int A = __byte_perm(wl, Cc, 0x5453);  // (p-1, p1)
+			const unsigned int D = __byte_perm(B, wr, 0x1412);   // (p2, p4)
+			hs[slot][0] = A + 2u * B + Cc;
+			hs[slot][1] = B + 2u * Cc + D;
+			hd[slot][0] = Cc + 0x01000100u - A;
+			hd[slot][1] = D + 0x01000100u - B;
 		};
+		// columns 1 <= x < W-1 of my four pixels, as masks over the (0, 2) and (1, 3) pairs
+		unsigned int cm[2] = { 0u, 0u };
+#pragma unroll
+		for (int i = 0; i < 4; ++i) if (xl + i >= 1 && xl + i < W - 1) cm[i & 1] |= 0xffffu << (16 * (i >> 1));
 		loadRow(rg0, 0);
 		loadRow(rg0 + 1, 1);
 #pragma unroll
@@ -219,20 +271,21 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 				loadRow(rg + 2, (j + 2) % 3);
 				const int a = j % 3, b = (j + 1) % 3, c = (j + 2) % 3;
 				const int y = y0 - 1 + rg;
-				const bool rowOk = (y >= 1 && y < H - 1);
-				unsigned int packed[4];
+				uint2 o = make_uint2(0u, 0u);
+				if (y >= 1 && y < H - 1) {
+					unsigned int g[2];
 #pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					const int x = xl + i;
-					const int gx = hd[a][i] + 2 * hd[b][i] + hd[c][i];
-					const int gy = hs[c][i] - hs[a][i];
-					const int g = abs(gx) + abs(gy);
-					// the NMS direction is NOT computed here: only the few per cent of the pixels with g > tLow need it, stage S4 recomputes gx / gy for those
-					packed[i] = (rowOk && x >= 1 && x < W - 1) ? static_cast<unsigned int>(g) : 0u;
+					for (int h = 0; h < 2; ++h) {
+						const unsigned int gx = hd[a][h] + 2u * hd[b][h] + hd[c][h];    // gx + 1024 in [4, 2044]
+						const unsigned int gy = hs[c][h] + 0x04000400u - hs[a][h];      // gy + 1024
+						const unsigned int ax = __vmaxu2(gx, 0x08000800u - gx);         // |gx| + 1024
+						const unsigned int ay = __vmaxu2(gy, 0x08000800u - gy);
+						// the NMS direction is NOT computed here: only the few per cent of the pixels with g > tLow need it, stage S4 recomputes gx / gy for those
+						g[h] = (ax + ay - 0x08000800u) & cm[h];
+					}
+					o.x = __byte_perm(g[0], g[1], 0x5410); // g0 | g1 << 16
+					o.y = __byte_perm(g[0], g[1], 0x7632); // g2 | g3 << 16
 				}
-				uint2 o;
-				o.x = packed[0] | (packed[1] << 16);
-				o.y = packed[2] | (packed[3] << 16);
 				*reinterpret_cast<uint2*>(&sGw[rg * 64 + lane * 2]) = o;
 			}
 		}
