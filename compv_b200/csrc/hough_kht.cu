@@ -90,7 +90,7 @@ __global__ void kht_bits_kernel(const uint8_t* __restrict__ edges, unsigned int*
 // over strings, instead of a load-after-store round trip through L2 between two walks.
 __global__ void __launch_bounds__(32)
 kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointers: no __restrict__ */, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll,
-	unsigned int* __restrict__ revAll, KhtFrame* frames, KhtGeom g)
+	unsigned int* __restrict__ revAll, KhtFrame* frames, KhtGeom g, int ahead)
 {
 	const int frame = blockIdx.x, lane = threadIdx.x;
 	const int W = g.W, H = g.H, WW = g.WW;
@@ -111,12 +111,12 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointe
 	// would pay an L2 round trip per new row.  The idle lanes therefore keep KHT_AHEAD rows below the scan line prefetched.
 	const char* bytes0 = reinterpret_cast<const char*>(base - KHT_PADR * WW);
 	const size_t bytesEnd = static_cast<size_t>(H + 2 * KHT_PADR) * WW * 4;
-	for (size_t o = static_cast<size_t>(lane) * 128; o < bytesEnd && o < static_cast<size_t>(KHT_AHEAD + KHT_PADR + 1) * WW * 4; o += 32 * 128)
+	for (size_t o = static_cast<size_t>(lane) * 128; o < bytesEnd && o < static_cast<size_t>(ahead + KHT_PADR + 1) * WW * 4; o += 32 * 128)
 		asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
 	for (int y = 1; y < H - 1; ++y) {
 		const unsigned int* row = base + static_cast<size_t>(y) * WW + 1; // word 0 of the image row
 		{
-			const size_t o = static_cast<size_t>(y + KHT_PADR + KHT_AHEAD) * WW * 4 + static_cast<size_t>(lane) * 128; // row y + KHT_AHEAD, one 128-byte line per lane
+			const size_t o = static_cast<size_t>(y + KHT_PADR + ahead) * WW * 4 + static_cast<size_t>(lane) * 128; // row y + ahead, one 128-byte line per lane
 			if (o < bytesEnd && lane * 128 < WW * 4 + 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(bytes0 + o));
 		}
 		for (int wb = 0; wb <= lastWord; wb += 32) {
@@ -145,6 +145,30 @@ kht_link_kernel(unsigned int* bitsAll /* read and written through derived pointe
 		}
 	}
 	if (lane == 0) { fr.nPos = nPos; fr.nStr = nStr; }
+}
+
+// ---- linking, 32 frames per warp (kht_walk.cuh: KhtLane) ----
+// Every lane links its own frame; the warp goes round one loop whose body is "scan two bitmap words" or "one step of the walk".  Used when a launch holds enough frames
+// for the batch to be the parallelism: per frame it issues ~1/20 of the instructions of the kernel above (whose 31 idle lanes still cost an issue slot each instruction),
+// at about the same latency per launch.  Same strings in the same order: the scan order, the walker and the records are the ones above.
+__global__ void __launch_bounds__(32)
+kht_link_lanes_kernel(unsigned int* bitsAll, ushort2* __restrict__ possAll, uint2* __restrict__ stringsAll, unsigned int* __restrict__ revAll, KhtFrame* frames, KhtGeom g, int batch)
+{
+	const int frame = blockIdx.x * 32 + threadIdx.x;
+	if (frame >= batch) return;
+	const int W = g.W, H = g.H, WW = g.WW;
+	KhtFrame& fr = frames[frame];
+	if (fr.skip) return;
+	unsigned int* base = bitsAll + (static_cast<size_t>(frame) * (H + 2 * KHT_PADR) + KHT_PADR) * WW; // padded word 0 of image row 0
+	unsigned int* poss = reinterpret_cast<unsigned int*>(possAll + fr.posOff);
+	unsigned long long* strs = reinterpret_cast<unsigned long long*>(stringsAll + fr.strOff);
+	unsigned int* revs = revAll + fr.strOff;
+	asm volatile("" : "+l"(base));
+	asm volatile("" : "+l"(poss));
+	KhtLane L;
+	L.start(H);
+	while (L.phase != 3) L.iterate(base, WW, W, H, g.minSize, poss, strs, revs);
+	fr.nPos = L.nPos; fr.nStr = L.nStr;
 }
 
 // the first walk of every string is stored in walk order: reverse it (houghkht.cxx:752-755).  One warp per string.
@@ -857,8 +881,18 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	  kht_offsets1_kernel<<<1, 256, 0, stream>>>(dEdgeCount, dFrames, dMeta, static_cast<int>(batch), g.minSize, h->posCapEl, h->strCapEl); }
 	CVB_LAUNCHED();
 	trace_mark(stream, "link>", h->traceSlot);
-	{ KernelScope ks_("kht_link", stream);
-	  kht_link_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g); }
+	{
+		// enough frames in one launch: one LANE per frame (issue-efficient); few frames: one WARP per frame (its 32 lanes share the seed scan: lower latency)
+		const char* ev = getenv("CVB200_KHT_LANES_MIN"); // read per call: tests switch it
+		const int lanesMin = (ev && *ev) ? atoi(ev) : INT_MAX; // measured (B200, 2048 1080p frames): 114 ms per launch against 18.2 ms for one warp per frame -- off unless asked for
+		const char* ea = getenv("CVB200_KHT_AHEAD");
+		const int ahead = (ea && *ea) ? atoi(ea) : KHT_AHEAD;
+		KernelScope ks_("kht_link", stream);
+		if (static_cast<long long>(batch) >= lanesMin)
+			kht_link_lanes_kernel<<<static_cast<unsigned>(div_up(batch, 32)), 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g, static_cast<int>(batch));
+		else
+			kht_link_kernel<<<B, 32, 0, stream>>>(h->bits.as<unsigned int>(), h->poss.as<ushort2>(), h->strings.as<uint2>(), h->strRev.as<unsigned int>(), dFrames, g, ahead);
+	}
 	CVB_LAUNCHED();
 	trace_mark(stream, "link<", h->traceSlot);
 	{ KernelScope ks_("kht_reverse", stream);

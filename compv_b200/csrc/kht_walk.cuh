@@ -179,4 +179,66 @@ KW_FN unsigned int kht_link_string(unsigned int* base, int WW, unsigned int seed
 	return static_cast<unsigned int>(n);
 }
 
+// ---- the whole linking pass of ONE frame as a state machine (one lane per frame: kht_link_lanes_kernel runs 32 frames per warp) ----
+// The one-warp-per-frame kernel spends 31 of its 32 lanes idle while lane 0 walks, so with many frames in flight it is bound by instruction issue (5.4 M
+// warp instructions per 1080p frame).  Here every lane owns a frame and all of them go round ONE loop whose body is "scan two bitmap words for the next seed" or
+// "take one step of the walk", so that one issued instruction serves up to 32 frames.  Same scan order, same walker, same output as kht_link_string driven by a raster scan.
+struct KhtLane {
+	KhtWalker wk;
+	unsigned int seedXY;
+	unsigned int n, rev;       // positions of the current string so far, length of its first walk
+	unsigned int nPos, nStr;   // positions / strings kept so far
+	int sy, sw;                // scan position: image row, (even) word of the row
+	int phase;                 // 0 = looking for a seed, 1 = first walk, 2 = second walk, 3 = frame finished
+	int emit;                  // store the current position before the next step (0 only for the step that opens the second walk)
+
+	KW_FN void start(int H)
+	{
+		wk.plo = 0; wk.phi = 0; wk.pend = 0; wk.T = wk.M = wk.B = wk.Fu = wk.Fd = 0; wk.c = 0; wk.ro = 0; wk.w0 = 0; wk.s = 0; wk.xy = 0;
+		seedXY = 0; n = 0; rev = 0; nPos = 0; nStr = 0; sy = 1; sw = 0; emit = 1;
+		phase = (H > 2) ? 0 : 3;
+	}
+	// One round of the loop.  base = padded word 0 of image row 0, poss = the frame's position pool (positions as x | y << 16), strs = its string records
+	// (begin | end << 32: a little-endian uint2 {begin, end}), revs = the length of every string's first walk.
+	KW_FN void iterate(unsigned int* base, int WW, int W, int H, unsigned int minSize, unsigned int* poss, unsigned long long* strs, unsigned int* revs)
+	{
+		if (phase == 0) {
+			const int lastWord = (W - 1) >> 5;
+			const unsigned int* row = base + sy * WW + 1;
+			unsigned int a = row[sw], b = row[sw + 1]; // sw + 1 may be the zero pad word right of the row
+			// seeds are interior columns only: x in [1, W-2]
+			if (sw == 0) a &= ~kw_colbit(0);
+			if (sw == lastWord) a &= ~kw_colbit((W - 1) & 31);
+			if (sw + 1 == lastWord) b &= ~kw_colbit((W - 1) & 31);
+			if (a | b) {
+				const int xr = sw * 32 + (a ? kw_first_col(a) : 32 + kw_first_col(b));
+				seedXY = static_cast<unsigned int>(xr) | (static_cast<unsigned int>(sy) << 16);
+				wk.xy = seedXY;
+				wk.centre(base, WW, 12); // a seed is the raster-first pixel left: nothing above it or to its left
+				n = 0; emit = 1; phase = 1;
+			}
+			else {
+				sw += 2;
+				if (sw > lastWord) { sw = 0; ++sy; if (sy >= H - 1) phase = 3; }
+			}
+		}
+		if (phase == 1 || phase == 2) {
+			if (emit) poss[nPos + n++] = wk.xy;
+			emit = 1;
+			if (!wk.step(base, WW)) {
+				if (phase == 1) { // the first walk is over: look around the seed for what it left (the seed itself is erased already)
+					rev = n;
+					wk.xy = seedXY;
+					wk.centre(base, WW, 16);
+					emit = 0; phase = 2;
+				}
+				else {
+					if (n >= minSize) { strs[nStr] = static_cast<unsigned long long>(nPos) | (static_cast<unsigned long long>(nPos + n) << 32); revs[nStr] = rev; ++nStr; nPos += n; }
+					phase = 0;
+				}
+			}
+		}
+	}
+};
+
 } // namespace cvb

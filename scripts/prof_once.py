@@ -13,7 +13,7 @@ import compv_b200 as cvb  # noqa: E402
 from compv_b200 import _ffi  # noqa: E402
 from frames import frame_g, frame_text  # noqa: E402
 
-W, H, B = 1920, 1080, 4
+W, H, B = 1920, 1080, int(os.environ.get("PROF_FRAMES", "4"))
 cvb.init(0)
 stream = torch.cuda.current_stream().cuda_stream
 frames = np.stack([frame_g(W, H, 12345 + k) for k in range(B)])
@@ -24,6 +24,8 @@ canny.set_preblur(5, 1.0)
 canny.process_dev(d_in, W, H, W, d_edges, batch=B, stream=stream)
 kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 100)
 print("kht lines", [len(x) for x in kht.process_dev(d_edges, W, H, W, batch=B, stream=stream)])
+if os.environ.get("PROF_NO_PLSL"):
+    sys.exit(0)
 text = np.stack([((frame_text(W, H, 20 + k) < 128) * 255).astype(np.uint8) for k in range(B)])
 ccl = cvb.CompVConnectedComponentLabeling.newObj(_ffi.PLSL_ID)
 print("plsl labels", ccl.process_dev(torch.from_numpy(text).cuda(), W, H, W, batch=B, stream=stream)[0])

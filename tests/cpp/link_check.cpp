@@ -76,6 +76,29 @@ static void link_bits(const std::vector<unsigned char>& e, int W, int H, unsigne
 	// whatever is left in the bitmap must be what the byte-map version leaves: checked through the strings only (every seedable pixel was consumed)
 }
 
+
+// ---- the same pass through the per-lane state machine (KhtLane: what kht_link_lanes_kernel runs, 32 frames per warp) ----
+static void link_lane(const std::vector<unsigned char>& e, int W, int H, unsigned int minSize, Strings& out)
+{
+	const int WW = (W + 31) / 32 + 2;
+	std::vector<unsigned int> bits(static_cast<size_t>(H + 2 * KHT_PADR) * WW, 0u);
+	unsigned int* base = bits.data() + static_cast<size_t>(KHT_PADR) * WW;
+	size_t edges = 0;
+	for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) if (e[static_cast<size_t>(y) * W + x]) { base[y * WW + 1 + (x >> 5)] |= kw_colbit(x & 31); ++edges; }
+	out.poss.assign(edges + 1, 0u);
+	std::vector<unsigned long long> strs(edges + 1, 0ull);
+	std::vector<unsigned int> revs(edges + 1, 0u);
+	KhtLane L;
+	L.start(H);
+	while (L.phase != 3) L.iterate(base, WW, W, H, minSize, out.poss.data(), strs.data(), revs.data());
+	for (unsigned int s = 0; s < L.nStr; ++s) {
+		const unsigned int b = static_cast<unsigned int>(strs[s]), en = static_cast<unsigned int>(strs[s] >> 32);
+		std::reverse(out.poss.begin() + b, out.poss.begin() + b + revs[s]); // kht_reverse_kernel on the device
+		out.begin.push_back(b); out.end.push_back(en);
+	}
+	out.poss.resize(L.nPos);
+}
+
 static unsigned int lcg(unsigned int& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 
 static bool same(const Strings& a, const Strings& b) { return a.poss == b.poss && a.begin == b.begin && a.end == b.end; }
@@ -103,6 +126,9 @@ int main(int argc, char** argv)
 		Strings got;
 		link_bits(e, W, H, minSize, got);
 		if (!same(want, got)) { ++bad; fprintf(stderr, "MISMATCH case %d: %dx%d kind %d minSize %u: strings %zu vs %zu\n", c, W, H, kind, minSize, want.begin.size(), got.begin.size()); }
+		Strings lane;
+		link_lane(e, W, H, minSize, lane);
+		if (!same(want, lane)) { ++bad; fprintf(stderr, "MISMATCH (lane state machine) case %d: %dx%d kind %d minSize %u: strings %zu vs %zu\n", c, W, H, kind, minSize, want.begin.size(), lane.begin.size()); }
 		totalStrings += want.begin.size(); totalPos += want.poss.size();
 	}
 	printf("link_check: %d cases, %zu strings, %zu positions, %d mismatches\n", cases, totalStrings, totalPos, bad);

@@ -127,6 +127,33 @@ def test_cuda_canny_then_kht_batched_on_device(cvb):
         same_lines(got[k], want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes_min", [1, 1 << 30])
+def test_cuda_kht_both_linking_kernels(cvb, lanes_min, monkeypatch):
+    """The linking stage has two kernels: one WARP per frame (few frames: the lanes share the seed scan) and one LANE per frame (kht_link_lanes_kernel, 32 frames per warp,
+    taken from CVB200_KHT_LANES_MIN frames per launch on).  Both must give the oracle's lines for every frame of a batch whose frames differ widely (empty, full,
+    text, long strings) and whose size is not a multiple of 32."""
+    import torch
+    from compv_b200 import _ffi
+    monkeypatch.setenv("CVB200_KHT_LANES_MIN", str(lanes_min))
+    w, h = 320, 200
+    maps = edge_maps(w, h) + [serpentine(w, h), frame_const(w, h, 0), frame_const(w, h, 255)]
+    maps += [canny_edges(frame_g(w, h, 4000 + k)) for k in range(70 - len(maps))]
+    maps = [maps[(7 * k) % len(maps)] for k in range(len(maps))]   # neighbours in a warp differ
+    batch = len(maps)
+    d_edges = torch.from_numpy(np.stack(maps)).cuda()
+    kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 30)
+    for _ in range(2):
+        got = kht.process_dev(d_edges, w, h, w, batch=batch, stream=torch.cuda.current_stream().cuda_stream)
+        for k in range(batch):
+            want, _ = oracle.hough_kht("orc", maps[k], 1.0, 1.0, 30)
+            same_lines(got[k], want)
+    # the per-frame host API with the lane kernel forced (a batch of one)
+    d = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 100)
+    for e in edge_maps(640, 480):
+        same_lines(d.process(e), oracle.hough_kht("orc", e, 1.0, 1.0, 100)[0])
+
+
 def serpentine(w, h):
     """One 8-connected string several thousand pixels long (longer than the linking kernel's shared-memory stage)."""
     e = np.zeros((h, w), np.uint8)
