@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=2048, help="frames per rank per step (the KHT linking stage runs one warp per frame: throughput grows with frames in flight)")
+    ap.add_argument("--frames", type=int, default=4096, help="frames per rank per step (the KHT linking stage runs one warp per frame: throughput grows with frames in flight; 4096 x 1080p = 8.5 GB)")
     ap.add_argument("--cpu-worker", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-rows", action="store_true", help="skip the extra BASELINE configurations (rows) and the single-frame latency")
     ap.add_argument("--cpu-frames", type=int, default=400, help="frames timed for cpu_baseline (rank 0, N=1)")
@@ -364,6 +364,7 @@ def main():
     frames = np.concatenate([make_frames(distinct, shard.weak_seed(12345, rank))] * ((B + distinct - 1) // distinct))[:B]  # (B, H, W) uint8: larger than the 126 MB L2
     h_in = torch.from_numpy(frames).pin_memory()
     d_in = h_in.cuda()
+    frames = frames[:8].copy()  # the CPU baseline below cycles 8 frames; the full batch now lives in the pinned buffer and on the device
     dete = cvb.CompVEdgeDete.newObj(cvb.CANNY_ID, TLOW, THIGH, KS)
     dete.set_preblur(BLUR, SIGMA)
     kht = cvb.CompVHough.newObj(cvb.HOUGHKHT_ID, 1.0, 1.0, KHT_THRESHOLD)

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "tma.cuh"
+#include "packed.cuh"
 
 namespace cvb {
 
@@ -67,48 +68,6 @@ __device__ __forceinline__ unsigned int pack4(unsigned int a, unsigned int b, un
 }
 
 
-// ---- packed arithmetic (sm_100a): two IEEE fp32 lanes per instruction (FFMA2 / FADD2 / FMUL2: each lane rounds exactly like the scalar instruction, so the
-// reference's fma chain is reproduced bit for bit at half the issue slots), and two 16-bit lanes in plain 32-bit integer adds (all intermediate values are kept non-negative by a bias).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(unsigned int lo, unsigned int hi)
-{
-	f32x2 r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-	return r;
-}
-__device__ __forceinline__ void unpk2(f32x2 v, unsigned int& lo, unsigned int& hi)
-{
-	asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
-{
-	f32x2 r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-	return r;
-}
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-__device__ __forceinline__ f32x2 fadd2_rz(f32x2 a, f32x2 b)
-{
-	f32x2 r;
-	asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-	return r;
-}
-// bytes ia of wa and ib of wb as the float pair (wa.byte[ia], wb.byte[ib])
-__device__ __forceinline__ f32x2 u8x2_to_f32x2(unsigned int wa, int ia, unsigned int wb, int ib, f32x2 negMagic)
-{
-	return fadd2(pk2(__byte_perm(wa, 0x4B000000u, 0x7440u | ia), __byte_perm(wb, 0x4B000000u, 0x7440u | ib)), negMagic);
-}
 
 template <int BKS>
 __global__ void __launch_bounds__(CF_THREADS, 3)
@@ -237,6 +196,10 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 	// ---- S3: Sobel 3x3 + L1 magnitude + direction code -> sG ----
 	int tLow = p.tLow, tHigh = p.tHigh;
 	if (p.thr) { const ushort2 t = p.thr[frame]; tLow = t.x; tHigh = t.y; }
+	// per-warp candidate queue of stage S4 (entries: row * 128 + column inside the g tile); every warp queues, tests and writes out the rows it computes g for
+	unsigned short* q = reinterpret_cast<unsigned short*>(sA + (G::OFF_Q - G::OFF_A)) + warp * (G::Q_WORDS_PER_WARP * 2);
+	unsigned int qn = 0; // warp-uniform
+	unsigned int* sOut = BKS ? sM : (sA + (G::OFF_M - G::OFF_A)); // class tile, 32 words per output row (only with a blur: without one there is no spare tile)
 	{
 		constexpr int RPW = (G::G_ROWS + CF_WARPS - 1) / CF_WARPS; // 8
 		const int rg0 = warp * RPW;
@@ -262,6 +225,11 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 		unsigned int cm[2] = { 0u, 0u };
 #pragma unroll
 		for (int i = 0; i < 4; ++i) if (xl + i >= 1 && xl + i < W - 1) cm[i & 1] |= 0xffffu << (16 * (i >> 1));
+		// NMS candidates (g > tLow) are queued right here, one ballot per pixel slot: adding 0x8000 - (tLow + 1) to a 16-bit half sets its top bit exactly when g > tLow
+		// (g <= 2040: nothing carries into the other half).  Lanes 0 and 31 hold halo columns only, rows 0 and G_ROWS-1 are halo rows.
+		const unsigned int candAdd = (0x8000u - static_cast<unsigned int>(min(tLow, 0x7ffe) + 1)) * 0x10001u;
+		const unsigned int candLane = (lane >= 1 && lane <= 30) ? 0x80008000u : 0u;
+		const unsigned int ltMask = (1u << lane) - 1u;
 		loadRow(rg0, 0);
 		loadRow(rg0 + 1, 1);
 #pragma unroll
@@ -285,42 +253,36 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 					}
 					o.x = __byte_perm(g[0], g[1], 0x5410); // g0 | g1 << 16
 					o.y = __byte_perm(g[0], g[1], 0x7632); // g2 | g3 << 16
+					if (rg >= 1 && rg <= CF_TH) { // warp-uniform
+						const unsigned int f[2] = { (g[0] + candAdd) & candLane, (g[1] + candAdd) & candLane };
+						const unsigned int e0 = static_cast<unsigned int>(rg * 128 + lane * 4);
+#pragma unroll
+						for (int i = 0; i < 4; ++i) {
+							const bool cand = (f[i & 1] & (0x8000u << (16 * (i >> 1)))) != 0u;
+							const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+							if (cand) q[qn + __popc(bal & ltMask)] = static_cast<unsigned short>(e0 + i);
+							qn += __popc(bal);
+						}
+					}
 				}
 				*reinterpret_cast<uint2*>(&sGw[rg * 64 + lane * 2]) = o;
+				if (BKS && rg >= 1 && rg <= CF_TH) sOut[(rg - 1) * CF_ROWW + lane] = 0; // the class tile starts out empty (sM is dead since the barrier before this stage)
 			}
 		}
 	}
 	__syncthreads();
 
 	// ---- S4: NMS on the unsuppressed g + classification -> global ----
-	// Only a few per cent of the pixels pass g > tLow, and they cluster on a few lanes: testing them where they lie keeps 1-2 lanes of a warp busy for tens of
-	// instructions per row (ncu: 70 of 130 lane-instructions per pixel).  Instead every warp (A) queues the candidates of its rows, (B) works the queue off with all 32
-	// lanes -- gradient recomputed from the blurred tile that is still resident, direction, the two neighbours along it -- writing the class byte into an output tile
-	// (the dead sM), and (C) streams its rows of that tile to global memory.
+	// Only ~13 % of the pixels pass g > tLow, and they cluster on a few lanes: testing them where they lie keeps 1-2 lanes of a warp busy for tens of
+	// instructions per row.  Instead every warp (A, done in S3) queued the candidates of its rows, now (B) works the queue off with all 32
+	// lanes -- gradient recomputed from the blurred tile that is still resident, direction, the two neighbours along it -- writing the class byte into the class
+	// tile (the dead sM), and (C) streams its rows of that tile to global memory.
 	{
+		constexpr int RPW = (G::G_ROWS + CF_WARPS - 1) / CF_WARPS; // 8: the same row ownership as S3
 		const unsigned short* sG = reinterpret_cast<const unsigned short*>(sGw);
 		uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
-		unsigned short* q = reinterpret_cast<unsigned short*>(sA + (G::OFF_Q - G::OFF_A)) + warp * (G::Q_WORDS_PER_WARP * 2);
-		unsigned int* qn = sA + (G::OFF_Q - G::OFF_A) + CF_WARPS * G::Q_WORDS_PER_WARP + warp;
-		unsigned int* sOut = BKS ? sM : (sA + (G::OFF_M - G::OFF_A)); // 32 words per output row; without blur sM's slot is unused but absent: see below
-		if (lane == 0) *qn = 0;
-		__syncwarp();
-		// (A)
-		for (int ro = warp; ro < CF_TH; ro += CF_WARPS) {
-			const int rg = ro + 1;
-			const uint2 gw = *reinterpret_cast<const uint2*>(&sGw[rg * 64 + lane * 2]);
-			const int g4[4] = { static_cast<int>(gw.x & 0xffffu), static_cast<int>(gw.x >> 16), static_cast<int>(gw.y & 0xffffu), static_cast<int>(gw.y >> 16) };
-			if (lane >= 1 && lane <= 30) { // lanes 0 and 31 hold halo columns only
-#pragma unroll
-				for (int i = 0; i < 4; ++i) {
-					if (g4[i] > tLow) q[atomicAdd(qn, 1u)] = static_cast<unsigned short>(rg * 128 + lane * 4 + i);
-				}
-			}
-			if (BKS) sOut[ro * CF_ROWW + lane] = 0;
-		}
-		__syncwarp();
 		// (B)
-		const unsigned int n = *qn;
+		const unsigned int n = qn;
 		constexpr int PB = (BKS ? CF_ROWW : CF_INW) * 4;
 		const unsigned char* tile = reinterpret_cast<const unsigned char*>(sA + (BKS ? 0 : woff));
 		unsigned char* outBytes = reinterpret_cast<unsigned char*>(sOut);
@@ -343,7 +305,8 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 				if (BKS) outBytes[(rg - 1) * (CF_ROWW * 4) + col] = c;
 				else { // no blurred tile, hence no spare tile: the few survivors go straight to global memory, after this warp's zero fill below (same warp, ordered by the __syncwarp + fence)
 					const int y = y0 + rg - 1, x = x0 - 4 + col;
-					if (col >= 4 && col < 124 && y < H && x < W) q[k] = static_cast<unsigned short>(idx | (c == CLS_STRONG ? 0x8000 : 0x4000));
+					if (y < H && x < W) q[k] = static_cast<unsigned short>(idx | (c == CLS_STRONG ? 0x8000 : 0x4000));
+					else q[k] = 0;
 					continue;
 				}
 			}
@@ -352,18 +315,18 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 		__syncwarp();
 		// (C)
 		const bool laneOut = (lane >= 1 && lane <= 30);
-		for (int ro = warp; ro < CF_TH; ro += CF_WARPS) {
-			const int y = y0 + ro;
-			if (y >= H) break; // warp-uniform
-			if (!laneOut || xl >= W) continue;
-			const unsigned int outw = BKS ? sOut[ro * CF_ROWW + lane] : 0u;
-			uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
-			if (p.vecStore && xl + 4 <= W) {
-				*reinterpret_cast<unsigned int*>(o) = outw;
-			}
-			else {
+		const int roBegin = max(warp * RPW - 1, 0), roEnd = min(warp * RPW + RPW - 1, CF_TH); // output rows ro = rg - 1 of my g rows
+		if (laneOut && xl < W) {
+			uint8_t* o = cls + static_cast<size_t>(y0 + roBegin) * p.stride + xl;
+			for (int ro = roBegin; ro < roEnd && y0 + ro < H; ++ro, o += p.stride) {
+				const unsigned int outw = BKS ? sOut[ro * CF_ROWW + lane] : 0u;
+				if (p.vecStore && xl + 4 <= W) {
+					*reinterpret_cast<unsigned int*>(o) = outw;
+				}
+				else {
 #pragma unroll
-				for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+					for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+				}
 			}
 		}
 		if (!BKS) {

@@ -155,23 +155,39 @@ __global__ void __launch_bounds__(MSER_BLOCK) mser_union_kernel(const uint8_t* _
 	const int nEdges = g.conn8 ? 8 : 4;
 	const int offs8[8] = { 1, 1 - g.S, -g.S, -g.S - 1, -1, g.S - 1, g.S + 1, g.S };
 	const int offs4[4] = { 1, -g.S, -1, g.S };
-	for (unsigned int i = i0 + blockIdx.x * MSER_BLOCK + threadIdx.x; i < i1; i += gridDim.x * MSER_BLOCK) {
-		const int p = order[i];
+	const unsigned int lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+	// warp-uniform trip count: the append to the absorbed list below is aggregated per warp (one atomicAdd on the shared counter per warp and edge instead of one per
+	// union: ~250 k same-address atomics per level were the bulk of this kernel's time)
+	for (unsigned int base = i0 + blockIdx.x * MSER_BLOCK; base < i1; base += gridDim.x * MSER_BLOCK) {
+		const unsigned int i = base + threadIdx.x;
+		const bool active = i < i1;
+		const int p = active ? order[i] : 0;
 		const int f = p / FP, idx = p - f * FP;
 		const uint8_t* frame = img + static_cast<size_t>(f) * g.framePitch;
 		for (int e = 0; e < nEdges; ++e) {
+			int gone = -1; // the root this thread's union removed, if any
 			const int q = idx + (g.conn8 ? offs8[e] : offs4[e]);
-			if (!mser_valid(g, q)) continue;
-			const int lq = frame[q];
-			if (lq > t || (lq == t && q > idx)) continue; // higher levels later; equal levels are united once, from the larger index
-			if (lq == t && q == idx - 1 && (idx % g.S) != 0) continue; // same row run: united by mser_runstart
-			int ra = uf_find(uf, p), rb = uf_find(uf, f * FP + q);
-			while (ra != rb) {
-				if (ra < rb) { const int tmp = ra; ra = rb; rb = tmp; }
-				const int old = atomicCAS(&uf[ra], ra, rb);
-				if (old == ra) { absorbed[atomicAdd(&cnt->absorbedCount, 1u)] = ra; break; }
-				ra = uf_find(uf, old);
-				rb = uf_find(uf, rb);
+			if (active && mser_valid(g, q)) {
+				const int lq = frame[q];
+				// higher levels later; equal levels are united once, from the larger index; the left neighbour of the same level was united by mser_runstart
+				if (!(lq > t || (lq == t && q > idx)) && !(lq == t && q == idx - 1 && (idx % g.S) != 0)) {
+					int ra = uf_find(uf, p), rb = uf_find(uf, f * FP + q);
+					while (ra != rb) {
+						if (ra < rb) { const int tmp = ra; ra = rb; rb = tmp; }
+						const int old = atomicCAS(&uf[ra], ra, rb);
+						if (old == ra) { gone = ra; break; }
+						ra = uf_find(uf, old);
+						rb = uf_find(uf, rb);
+					}
+				}
+			}
+			__syncwarp();
+			const unsigned int bal = __ballot_sync(0xffffffffu, gone >= 0);
+			if (bal) {
+				unsigned int at = 0;
+				if (lane == static_cast<unsigned int>(__ffs(bal) - 1)) at = atomicAdd(&cnt->absorbedCount, static_cast<unsigned int>(__popc(bal)));
+				at = __shfl_sync(0xffffffffu, at, __ffs(bal) - 1);
+				if (gone >= 0) absorbed[at + __popc(bal & ltMask)] = gone;
 			}
 		}
 	}
@@ -182,15 +198,25 @@ __global__ void __launch_bounds__(MSER_BLOCK) mser_claim_kernel(const int* __res
 	int* __restrict__ ownCnt, int* __restrict__ nodeRoot, MserCounters* cnt, int t)
 {
 	const unsigned int i0 = cnt->levelStart[t], i1 = cnt->levelStart[t + 1];
-	for (unsigned int i = i0 + blockIdx.x * MSER_BLOCK + threadIdx.x; i < i1; i += gridDim.x * MSER_BLOCK) {
-		const int p = order[i];
-		const int r = uf_find(uf, p);
+	const unsigned int lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+	for (unsigned int base = i0 + blockIdx.x * MSER_BLOCK; base < i1; base += gridDim.x * MSER_BLOCK) { // warp-uniform trip count: node numbers are reserved once per warp
+		const unsigned int i = base + threadIdx.x;
+		const bool active = i < i1;
+		const int r = active ? uf_find(uf, order[i]) : -1 - static_cast<int>(lane); // inactive lanes: distinct keys nobody shares
 		// lanes of the warp that found the same root speak once (flat areas put whole warps on one root)
-		const unsigned int peers = __match_any_sync(__activemask(), r);
-		if ((__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31)) {
+		const unsigned int peers = __match_any_sync(0xffffffffu, r);
+		bool fresh = false;
+		if (active && (__ffs(peers) - 1) == static_cast<int>(lane)) {
 			atomicAdd(&ownCnt[r], __popc(peers));
-			if (atomicExch(&stamp[r], t) != t) {
-				const int n = static_cast<int>(atomicAdd(&cnt->nodeCount, 1u));
+			fresh = atomicExch(&stamp[r], t) != t;
+		}
+		const unsigned int bal = __ballot_sync(0xffffffffu, fresh);
+		if (bal) {
+			unsigned int at = 0;
+			if (lane == static_cast<unsigned int>(__ffs(bal) - 1)) at = atomicAdd(&cnt->nodeCount, static_cast<unsigned int>(__popc(bal)));
+			at = __shfl_sync(0xffffffffu, at, __ffs(bal) - 1);
+			if (fresh) {
+				const int n = static_cast<int>(at + __popc(bal & ltMask));
 				nodeRoot[n] = r;
 				pendingNode[r] = n;
 			}
@@ -419,14 +445,19 @@ static int mser_chunk(cvb200_ccl* c, const uint8_t* img, size_t width, size_t he
 	  mser_scatter_kernel<<<MSER_GRID, 256, 0, stream>>>(img, dLevelCursor, c->mOrder.as<int>(), g); }
 	CVB_LAUNCHED(); g_launches.fetch_add(2, std::memory_order_relaxed);
 	{
-		KernelScope ks_("mser_levels", stream);
+		static const bool split = getenv("CVB200_MSER_SPLIT") != nullptr; // profiling aid: one scope per kernel of a level instead of one for the loop
+		KernelScope ks_(split ? "mser_levels_all" : "mser_levels", stream);
 		for (int t = 0; t < 256; ++t) {
-			mser_union_kernel<<<MSER_GRID, MSER_BLOCK, 0, stream>>>(img, c->mOrder.as<int>(), uf, c->mAbsorbed.as<int>(), dCnt, t, g);
-			mser_claim_kernel<<<MSER_GRID, MSER_BLOCK, 0, stream>>>(c->mOrder.as<int>(), uf, c->mStamp.as<int>(), c->mPending.as<int>(), c->mOwnCnt.as<int>(), c->mNodeRoot.as<int>(), dCnt, t);
+			{ KernelScope k1(split ? "mser_union" : nullptr, split ? stream : nullptr, split);
+			mser_union_kernel<<<MSER_GRID, MSER_BLOCK, 0, stream>>>(img, c->mOrder.as<int>(), uf, c->mAbsorbed.as<int>(), dCnt, t, g); }
+			{ KernelScope k2(split ? "mser_claim" : nullptr, split ? stream : nullptr, split);
+			mser_claim_kernel<<<MSER_GRID, MSER_BLOCK, 0, stream>>>(c->mOrder.as<int>(), uf, c->mStamp.as<int>(), c->mPending.as<int>(), c->mOwnCnt.as<int>(), c->mNodeRoot.as<int>(), dCnt, t); }
+			{ KernelScope k3(split ? "mser_attach" : nullptr, split ? stream : nullptr, split);
 			mser_attach_kernel<<<MSER_GRID, MSER_BLOCK, 0, stream>>>(c->mOrder.as<int>(), uf, c->mPending.as<int>(), c->mPixNode.as<int>(), c->mAbsorbed.as<int>(), c->mCompSize.as<int>(),
-				c->mAddSize.as<int>(), c->mTopNode.as<int>(), c->mNodeParent.as<int>(), dCnt, t);
+				c->mAddSize.as<int>(), c->mTopNode.as<int>(), c->mNodeParent.as<int>(), dCnt, t); }
+			{ KernelScope k4(split ? "mser_finalize" : nullptr, split ? stream : nullptr, split);
 			mser_finalize_kernel<<<MSER_GRID, MSER_BLOCK, 0, stream>>>(c->mNodeRoot.as<int>(), c->mCompSize.as<int>(), c->mAddSize.as<int>(), c->mOwnCnt.as<int>(), c->mTopNode.as<int>(),
-				c->mNodeParent.as<int>(), c->mNodeArea.as<int>(), c->mNodeOwn.as<int>(), c->mNodeLevel.as<int>(), dCnt, t);
+				c->mNodeParent.as<int>(), c->mNodeArea.as<int>(), c->mNodeOwn.as<int>(), c->mNodeLevel.as<int>(), dCnt, t); }
 		}
 	}
 	CVB_LAUNCHED(); g_launches.fetch_add(1023, std::memory_order_relaxed);

@@ -42,6 +42,7 @@ void profile_mark(const char* name, cudaStream_t stream, bool begin);
 struct KernelScope {
 	const char* name; cudaStream_t stream; bool on;
 	KernelScope(const char* n, cudaStream_t s) : name(n), stream(s), on(g_profiling.load(std::memory_order_relaxed) != 0) { if (on) profile_mark(name, stream, true); }
+	KernelScope(const char* n, cudaStream_t s, bool enable) : name(n), stream(s), on(enable && g_profiling.load(std::memory_order_relaxed) != 0) { if (on) profile_mark(name, stream, true); }
 	~KernelScope() { if (on) profile_mark(name, stream, false); }
 };
 

@@ -20,7 +20,8 @@ using namespace cvb;
 namespace {
 
 struct PipeSlot {
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;    // the stream of the current call: one of the two below
+	cudaStream_t streamDev = nullptr, streamHost = nullptr; // device frames: earlier slots have the higher stream priority; host frames: later slots (see run_pipeline)
 	cudaEvent_t evIn = nullptr;       // this slot's upload has landed
 	cvb200_edge_dete canny;
 	cvb200_hough hough;
@@ -139,40 +140,51 @@ int run_pipeline(Job& j, cudaStream_t callerStream)
 	j.sub = sub;
 	const size_t nSub = div_up(j.batch, sub);
 	const size_t nSlots = std::min(nSlotsWanted, nSub);
-	while (st.slots.size() < nSlots) {
+	// Stream priorities are fixed when a stream is created, so every slot owns one stream per mode (scratch and detectors are shared: a call drains all slots before it returns):
+	//   * device frames: everything is queued at once on streams of EQUAL priority.  Measured (B200, 2048 frames, 6 slots): 44.2 ms per step with equal priorities against
+	//     49.3 ms with "earlier slots first" and 49.7 ms with "later slots first".  The linking kernel is a latency chain per warp: sharing an SM with Canny blocks slows
+	//     both down by more than the overlap wins, so the best schedule is the one where the Canny kernels of all slots finish together and the linking kernels then
+	//     run side by side (more linking warps per scheduler = better issue utilisation), the short voting / peak stages filling the gaps;
+	//   * host frames: the upload paces the call and the GPU is not full; what counts is how soon after the LAST upload the last sub-batch is done, so the newest
+	//     sub-batch must not queue behind its predecessors: later slots get the higher priority and the ring is rotated so that the last sub-batch runs on the last slot
+	//     (trace of 2048 host frames before this: the last sub-batch's Canny took 10 ms instead of 2.8).
+	std::vector<PipeSlot*>& slots = st.slots;
+	while (slots.size() < nSlots) {
 		PipeSlot* s = new (std::nothrow) PipeSlot();
 		CVB_REQUIRE(s, CVB200_E_OUT_OF_MEMORY);
-		// Earlier slots get the higher priority: the Canny kernels of all slots are queued at once and would otherwise share the SMs evenly and all finish
-		// together; with priorities slot 0's Canny finishes first and its linking kernel (a long latency chain) starts while the later slots are still in Canny.
 		int prLo = 0, prHi = 0;
 		CVB_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi)); // numerically lower = higher priority
-		int pr = prHi + static_cast<int>(st.slots.size());
-		if (pr > prLo) pr = prLo;
-		if (env_int("CVB200_PIPE_PRIORITIES", 1) == 0) pr = prLo;
-		CVB_CUDA(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, pr));
+		const int idx = static_cast<int>(slots.size());
+		const bool flat = env_int("CVB200_PIPE_PRIORITIES", 1) == 0;
+		const int devMode = env_int("CVB200_PIPE_PRIO_DEV", 0); // 0 = equal (default), 1 = earlier slots higher, 2 = later slots higher
+		CVB_CUDA(cudaStreamCreateWithPriority(&s->streamDev, cudaStreamNonBlocking, (flat || devMode == 0) ? prLo : devMode == 1 ? std::min(prLo, prHi + idx) : std::max(prHi, prLo - idx)));
+		CVB_CUDA(cudaStreamCreateWithPriority(&s->streamHost, cudaStreamNonBlocking, flat ? prLo : std::max(prHi, prLo - idx)));
 		CVB_CUDA(cudaEventCreateWithFlags(&s->evIn, cudaEventDisableTiming));
 		s->hough.lastGs = 1.0;
-		st.slots.push_back(s);
+		slots.push_back(s);
 	}
-	for (size_t i = 0; i < nSlots; ++i) { copy_params(st.slots[i]->canny, *j.canny); copy_params(st.slots[i]->hough, *j.hough); st.slots[i]->busy = false; }
+	for (size_t i = 0; i < nSlots; ++i) slots[i]->stream = j.onHost ? slots[i]->streamHost : slots[i]->streamDev;
+	for (size_t i = 0; i < nSlots; ++i) { copy_params(slots[i]->canny, *j.canny); copy_params(slots[i]->hough, *j.hough); slots[i]->busy = false; }
 	if (!j.onHost) CVB_CUDA(cudaEventRecord(st.evStart, callerStream));
+	// sub-batch k runs on slot (k + rot) % nSlots; host frames: rot puts the last sub-batch on the last (highest-priority) slot
+	const size_t rot = j.onHost ? (nSlots - 1 + nSlots - ((nSub - 1) % nSlots)) % nSlots : 0;
 	int rc = CVB200_S_OK;
 	for (size_t k = 0; k < nSub && rc == CVB200_S_OK; ++k) {
-		PipeSlot& s = *st.slots[k % nSlots];
+		PipeSlot& s = *slots[(k + rot) % nSlots];
 		rc = slot_finish(s, j); // the sub-batch that used this slot nSlots steps ago
 		if (rc == CVB200_S_OK) { const size_t f0 = k * sub; rc = slot_enqueue(st, s, j, f0, std::min(sub, j.batch - f0)); }
 	}
 	// drain in submission order (also on errors: nothing may stay in flight on the cached streams)
 	for (size_t k = 0; k < nSlots; ++k) {
-		PipeSlot& s = *st.slots[(nSub + k) % nSlots];
+		PipeSlot& s = *slots[(nSub + k + rot) % nSlots];
 		const int r2 = (rc == CVB200_S_OK) ? slot_finish(s, j) : (cudaStreamSynchronize(s.stream), CVB200_S_OK);
 		if (rc == CVB200_S_OK) rc = r2;
 		s.busy = false;
 	}
 	trace_dump(j.onHost ? "canny+kht pipeline, host frames" : "canny+kht pipeline, device frames");
 	if (rc == CVB200_S_OK) {
-		j.hough->lastGs = st.slots[(nSub - 1) % nSlots]->hough.lastGs;
-		for (size_t i = 0; i < nSlots; ++i) if (j.canny->hystRounds < st.slots[i]->canny.hystRounds) j.canny->hystRounds = st.slots[i]->canny.hystRounds;
+		j.hough->lastGs = slots[(nSub - 1 + rot) % nSlots]->hough.lastGs;
+		for (size_t i = 0; i < nSlots; ++i) if (j.canny->hystRounds < slots[i]->canny.hystRounds) j.canny->hystRounds = slots[i]->canny.hystRounds;
 	}
 	return rc;
 }
