@@ -414,15 +414,20 @@ __global__ void canny_finalize_kernel(uint8_t* cls, int W, int H, size_t stride,
 
 // The same pass that also emits the KHT linking bitmap (1 bit per pixel, bit 31 = leftmost column of a word, two zero rows / one zero word of padding: kht_walk.cuh)
 // and counts the edge pixels of each frame.  32 pixels per thread.
-__global__ void __launch_bounds__(128) canny_finalize_bits_kernel(uint8_t* cls, int W, int H, size_t stride, size_t framePitch, unsigned int* __restrict__ bits, int WW, int padRows,
+// Block = 32 x 8 threads: a warp covers 32 words (1024 pixels) of one row, a block 8 rows (one block per row left most of a 128-thread block idle at 1920 columns
+// and made 4.4 M blocks per 4096 frames); one atomic per block on the frame's edge counter.
+__global__ void __launch_bounds__(256) canny_finalize_bits_kernel(uint8_t* cls, int W, int H, size_t stride, size_t framePitch, unsigned int* __restrict__ bits, int WW, int padRows,
 	unsigned int* __restrict__ edgeCount)
 {
-	const int y = blockIdx.y, frame = blockIdx.z;
+	__shared__ unsigned int sCount;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y, frame = blockIdx.z;
+	if (threadIdx.x == 0 && threadIdx.y == 0) sCount = 0;
+	__syncthreads();
 	uint8_t* row = cls + frame * framePitch + static_cast<size_t>(y) * stride;
 	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
 	const int x = wi * 32;
 	unsigned int word = 0;
-	if (x < W) {
+	if (x < W && y < H) {
 		auto fix = [](unsigned int w) { const unsigned int keep = (w & 0x01010101u) * 0xffu; return w & keep; };
 		auto nz4 = [](unsigned int w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }; // after fix() a byte is 0x00 or 0xff: bit 0 of each byte -> 4 bits
 		if (x + 32 <= W && ((reinterpret_cast<uintptr_t>(row + x) & 15) == 0)) {
@@ -446,7 +451,9 @@ __global__ void __launch_bounds__(128) canny_finalize_bits_kernel(uint8_t* cls, 
 	}
 	unsigned int c = __popc(word);
 	for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&edgeCount[frame], c);
+	if (threadIdx.x == 0 && c) atomicAdd(&sCount, c);
+	__syncthreads();
+	if (threadIdx.x == 0 && threadIdx.y == 0 && sCount) atomicAdd(&edgeCount[frame], sCount);
 }
 
 // sum of a u8 frame (CompVMathUtils::sum<uint8_t,uint32_t>, canny_dete.cxx:243) -> PERCENT_OF_MEAN thresholds (:253-258)
@@ -765,9 +772,9 @@ int cvb::edge_enqueue(cvb200_edge_dete* d, const uint8_t* image, size_t width, s
 	dim3 fg(static_cast<unsigned>(div_up(div_up(width, 16), 128)), static_cast<unsigned>(height), static_cast<unsigned>(batch));
 	CVB_REQUIRE(fg.y <= 65535, CVB200_E_OUT_OF_BOUND);
 	if (d->khtBits) {
-		dim3 bg(static_cast<unsigned>(div_up(div_up(width, 32), 128)), static_cast<unsigned>(height), static_cast<unsigned>(batch));
+		dim3 bg(static_cast<unsigned>(div_up(div_up(width, 32), 32)), static_cast<unsigned>(div_up(height, 8)), static_cast<unsigned>(batch));
 		KernelScope ks_("canny_finalize", stream);
-		canny_finalize_bits_kernel<<<bg, 128, 0, stream>>>(edges, p.W, p.H, stride, framePitch, d->khtBits, d->khtWW, 2, d->khtEdgeCount);
+		canny_finalize_bits_kernel<<<bg, dim3(32, 8), 0, stream>>>(edges, p.W, p.H, stride, framePitch, d->khtBits, d->khtWW, 2, d->khtEdgeCount);
 	}
 	else {
 		KernelScope ks_("canny_finalize", stream);

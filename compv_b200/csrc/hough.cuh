@@ -11,6 +11,7 @@ struct cvb200_hough {
 	bool x86Simd;
 	double lastGs;
 	// KHT scratch (hough_kht.cu)
+	int sortItemsHint = 8192;  // cells of the largest frame seen by the previous call (sizes the shared memory of the peak sort)
 	cvb::DevBuf sortItems, sortLists, sortRanges, dLines, dCounts, tabs;
 	cvb::HostBuf hTabs;
 	size_t posCapEl = 0, strCapEl = 0, voteCapEl = 0;   // element capacities of the shared pools (grow-only)

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) kht_row_offsets_kernel(unsigned int* __re
 	if (threadIdx.x == 0) frames[frame].nVotes = carry;
 }
 
-struct KhtMeta { unsigned int overflow; unsigned int pad; unsigned long long needPos, needStr, needVotes; };
+struct KhtMeta { unsigned int overflow; unsigned int maxVotes /* largest per-frame cell count: sizes the next call's shared-memory sort */; unsigned long long needPos, needStr, needVotes; };
 
 // per-frame offsets into the position / string pools from the edge counts (one block; batch frames)
 __global__ void __launch_bounds__(256) kht_offsets1_kernel(const unsigned int* __restrict__ edgeCount, KhtFrame* frames, KhtMeta* meta, int batch, unsigned int minSize,
@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(256) kht_offsets2_kernel(KhtFrame* frames, Kht
 		const unsigned int e = block_scan_256(c, sWarp, &t);
 		if (f < batch) frames[f].voteOff = run + e;
 		run += t;
+		if (c) atomicMax(&meta->maxVotes, c);
 	}
 	if (threadIdx.x == 0) { meta->needVotes = run + 1; if (run + 1 > voteCap) meta->overflow |= 2u; }
 }
@@ -693,7 +694,7 @@ __device__ int ksort_warp_partition(sse_item* a, int first, int last, IDX* Ls, I
 __global__ void __launch_bounds__(KSORT_THREADS)
 kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict__ itemsAll, unsigned int* __restrict__ listsAll, int* __restrict__ rangesAll, int* __restrict__ accAll,
 	const double* __restrict__ rhoTab, const double* __restrict__ thetaTab, cvb200_hough_line_t* __restrict__ lines, unsigned long long capacity, unsigned long long* __restrict__ counts,
-	const KhtFrame* frames, const KhtMeta* meta, KhtGeom g, unsigned int lim)
+	const KhtFrame* frames, const KhtMeta* meta, KhtGeom g, unsigned int lim, int smemItems)
 {
 	extern __shared__ __align__(16) unsigned char ksortSmem[];
 	__shared__ unsigned int sWarp[9];
@@ -704,9 +705,9 @@ kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict
 	const int nv = static_cast<int>(fr.nVotes);
 	if (nv == 0) { if (tid == 0) counts[frame] = 0; return; }
 	const KhtVote* votes = votesAll + fr.voteOff;
-	const bool inSmem = nv <= KSORT_SMEM_ITEMS;       // block-uniform
+	const bool inSmem = nv <= smemItems;               // block-uniform
 	sse_item* a; unsigned int* Ls = nullptr; unsigned int* Rs = nullptr; unsigned short* Ls16 = nullptr; unsigned short* Rs16 = nullptr;
-	if (inSmem) { a = reinterpret_cast<sse_item*>(ksortSmem); Ls16 = reinterpret_cast<unsigned short*>(a + KSORT_SMEM_ITEMS); Rs16 = Ls16 + KSORT_SMEM_ITEMS; }
+	if (inSmem) { a = reinterpret_cast<sse_item*>(ksortSmem); Ls16 = reinterpret_cast<unsigned short*>(a + smemItems); Rs16 = Ls16 + smemItems; }
 	else { a = itemsAll + fr.voteOff; Ls = listsAll + 2 * fr.voteOff; Rs = Ls + nv; }
 	for (int i = tid; i < nv; i += KSORT_THREADS) a[i] = (static_cast<sse_item>(static_cast<unsigned int>(votes[i].count)) << 32) | static_cast<unsigned int>(i);
 	__syncthreads();
@@ -930,12 +931,15 @@ int cvb::kht_enqueue(cvb200_hough* h, const uint8_t* edges, size_t width, size_t
 	CVB_LAUNCHED();
 	{
 		static std::atomic<unsigned int> attrSet{0};
-		const int smem = KSORT_SMEM_ITEMS * (8 + 2 + 2);
-		CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(kht_peaks_sort_kernel), smem, attrSet));
+		// shared memory per CTA follows the largest frame of the previous call on this object (5.7 k cells for the 1080p bench frames: 3 CTAs per SM instead of the 2 that
+		// the full 96 KB allow); a frame with more cells than that sorts in global memory
+		const int smemItems = std::min(KSORT_SMEM_ITEMS, std::max(1024, h->sortItemsHint));
+		const int smem = smemItems * (8 + 2 + 2);
+		CVB_CHECK(set_max_smem_once(reinterpret_cast<const void*>(kht_peaks_sort_kernel), KSORT_SMEM_ITEMS * (8 + 2 + 2), attrSet));
 		const unsigned int lim = (h->maxLines <= 0) ? static_cast<unsigned int>(INT_MAX) : static_cast<unsigned int>(h->maxLines);
 		KernelScope ks_("kht_peaks_sort", stream);
 		kht_peaks_sort_kernel<<<B, KSORT_THREADS, smem, stream>>>(h->votes.as<KhtVote>(), h->sortItems.as<sse_item>(), h->sortLists.as<unsigned int>(), h->sortRanges.as<int>(), h->acc.as<int>(),
-			dRhoTab, dThetaTab, h->dLines.as<cvb200_hough_line_t>(), static_cast<unsigned long long>(capacity), h->dCounts.as<unsigned long long>(), dFrames, dMeta, g, lim);
+			dRhoTab, dThetaTab, h->dLines.as<cvb200_hough_line_t>(), static_cast<unsigned long long>(capacity), h->dCounts.as<unsigned long long>(), dFrames, dMeta, g, lim, smemItems);
 	}
 	CVB_LAUNCHED();
 	// results that the host always needs: the per-frame line counts + the overflow flag + the last frame's record (Gs)
@@ -972,6 +976,7 @@ int cvb::kht_finish(cvb200_hough* h, cvb200_hough_line_t* lines, size_t capacity
 	const size_t batch = h->pendBatch;
 	CVB_CUDA(cudaStreamSynchronize(stream));
 	const KhtMeta* m = h->hFrames.as<KhtMeta>();
+	if (m->maxVotes) h->sortItemsHint = static_cast<int>(std::min<unsigned int>(KSORT_SMEM_ITEMS, ((m->maxVotes + m->maxVotes / 16 + 255u) / 256u) * 256u));
 	if (m->overflow) {
 		if (m->overflow & 1u) { h->posCapEl = std::max<size_t>(h->posCapEl, static_cast<size_t>(m->needPos + m->needPos / 4 + 1024)); h->strCapEl = std::max<size_t>(h->strCapEl, static_cast<size_t>(m->needStr + m->needStr / 4 + 1024)); }
 		if (m->overflow & 2u) h->voteCapEl = std::max<size_t>(h->voteCapEl, static_cast<size_t>(m->needVotes + m->needVotes / 4 + 1024));
