@@ -198,7 +198,7 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 	if (p.thr) { const ushort2 t = p.thr[frame]; tLow = t.x; tHigh = t.y; }
 	// per-warp candidate queue of stage S4 (entries: row * 128 + column inside the g tile); every warp queues, tests and writes out the rows it computes g for
 	unsigned short* q = reinterpret_cast<unsigned short*>(sA + (G::OFF_Q - G::OFF_A)) + warp * (G::Q_WORDS_PER_WARP * 2);
-	unsigned int qn = 0; // warp-uniform
+	unsigned int candWord = 0; // lane 4j + i: which lanes hold a candidate at pixel slot i of the warp's j-th g row (RPW = 8 rows x 4 slots = 32 lanes)
 	unsigned int* sOut = BKS ? sM : (sA + (G::OFF_M - G::OFF_A)); // class tile, 32 words per output row (only with a blur: without one there is no spare tile)
 	{
 		constexpr int RPW = (G::G_ROWS + CF_WARPS - 1) / CF_WARPS; // 8
@@ -229,7 +229,6 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 		// (g <= 2040: nothing carries into the other half).  Lanes 0 and 31 hold halo columns only, rows 0 and G_ROWS-1 are halo rows.
 		const unsigned int candAdd = (0x8000u - static_cast<unsigned int>(min(tLow, 0x7ffe) + 1)) * 0x10001u;
 		const unsigned int candLane = (lane >= 1 && lane <= 30) ? 0x80008000u : 0u;
-		const unsigned int ltMask = (1u << lane) - 1u;
 		loadRow(rg0, 0);
 		loadRow(rg0 + 1, 1);
 #pragma unroll
@@ -255,13 +254,10 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 					o.y = __byte_perm(g[0], g[1], 0x7632); // g2 | g3 << 16
 					if (rg >= 1 && rg <= CF_TH) { // warp-uniform
 						const unsigned int f[2] = { (g[0] + candAdd) & candLane, (g[1] + candAdd) & candLane };
-						const unsigned int e0 = static_cast<unsigned int>(rg * 128 + lane * 4);
 #pragma unroll
-						for (int i = 0; i < 4; ++i) {
-							const bool cand = (f[i & 1] & (0x8000u << (16 * (i >> 1)))) != 0u;
-							const unsigned int bal = __ballot_sync(0xffffffffu, cand);
-							if (cand) q[qn + __popc(bal & ltMask)] = static_cast<unsigned short>(e0 + i);
-							qn += __popc(bal);
+						for (int i = 0; i < 4; ++i) { // lane 4j + i keeps the candidate mask of (my j-th row, pixel slot i): expanded into the queue once, in S4
+							const unsigned int bal = __ballot_sync(0xffffffffu, f[i & 1] & (0x8000u << (16 * (i >> 1))));
+							if (lane == 4 * j + i) candWord = bal;
 						}
 					}
 				}
@@ -274,15 +270,27 @@ canny_front_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastPara
 
 	// ---- S4: NMS on the unsuppressed g + classification -> global ----
 	// Only ~13 % of the pixels pass g > tLow, and they cluster on a few lanes: testing them where they lie keeps 1-2 lanes of a warp busy for tens of
-	// instructions per row.  Instead every warp (A, done in S3) queued the candidates of its rows, now (B) works the queue off with all 32
+	// instructions per row.  Instead every warp (A) turns the candidate masks of its rows (ballots taken in S3) into a queue, (B) works the queue off with all 32
 	// lanes -- gradient recomputed from the blurred tile that is still resident, direction, the two neighbours along it -- writing the class byte into the class
 	// tile (the dead sM), and (C) streams its rows of that tile to global memory.
 	{
 		constexpr int RPW = (G::G_ROWS + CF_WARPS - 1) / CF_WARPS; // 8: the same row ownership as S3
 		const unsigned short* sG = reinterpret_cast<const unsigned short*>(sGw);
 		uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
+		// (A) expand the candidate masks into the queue: an exclusive prefix of the per-lane counts, then every lane writes out the set bits of its word
+		unsigned int n;
+		{
+			const unsigned int c = __popc(candWord);
+			unsigned int pre = c;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += t; }
+			n = __shfl_sync(0xffffffffu, pre, 31);
+			unsigned int pos = pre - c;
+			const unsigned int eBase = static_cast<unsigned int>((warp * RPW + (lane >> 2)) * 128 + (lane & 3)); // row of the word, pixel slot
+			for (unsigned int w = candWord; w; w &= w - 1) q[pos++] = static_cast<unsigned short>(eBase + 4u * static_cast<unsigned int>(__ffs(w) - 1));
+			__syncwarp();
+		}
 		// (B)
-		const unsigned int n = qn;
 		constexpr int PB = (BKS ? CF_ROWW : CF_INW) * 4;
 		const unsigned char* tile = reinterpret_cast<const unsigned char*>(sA + (BKS ? 0 : woff));
 		unsigned char* outBytes = reinterpret_cast<unsigned char*>(sOut);

@@ -41,7 +41,7 @@ struct MserGeom {
 struct MserCounters { unsigned int nodeCount, absorbedCount, regionCount, pad; unsigned int levelStart[257], levelNodeStart[257], levelAbsStart[257]; };
 struct MserRegion { int frame, level, root, off, area, node; };
 
-#define MSER_GRID 592
+#define MSER_GRID 1184 // 8 CTAs of 256 threads per SM: the level kernels are chains of dependent L2 / HBM accesses (ncu: 27 warps stalled on the long scoreboard per issue), more of them in flight is what helps
 #define MSER_BLOCK 256
 
 __device__ __forceinline__ bool mser_valid(const MserGeom& g, int idx) { return idx >= 0 && idx < g.H * g.S && (idx % g.S) < g.W; }
