@@ -82,11 +82,13 @@ def test_gauss_kernels(cvb):
 @pytest.mark.parametrize("ks", [3, 5])
 @pytest.mark.parametrize("border", [0, 1, 2])
 @pytest.mark.parametrize("w,h,stride", [(120, 60, 128), (121, 61, 128), (240, 119, 240), (250, 125, 256), (7, 9, 16), (333, 77, 384)])
-def test_convlt1_8u32f8u_tma_path(cvb, ks, border, w, h, stride):
-    """16-byte aligned strides take the TMA-staged 4-px-per-lane kernel: every border type, tile edges, negative taps (clamping), tiny frames."""
+@pytest.mark.parametrize("packed", [False, True])
+def test_convlt1_8u32f8u_tma_path(cvb, ks, border, w, h, stride, packed):
+    """16-byte aligned strides take the TMA-staged 4-px-per-lane kernel: every border type, tile edges, tiny frames.  Two instances: negative taps keep the scalar
+    chain with the clamp; two normalised Gaussians (clamp is a no-op) take the packed FFMA2 / FADD2 chain."""
     rng = np.random.default_rng(ks * 100 + border * 10 + w)
     img = frame_uniform(w, h, int(rng.integers(1 << 30)), stride)
-    vt = (rng.random(ks).astype(np.float32) - np.float32(0.3))
+    vt = oracle.gauss_kernel("orc", ks, 0.7) if packed else (rng.random(ks).astype(np.float32) - np.float32(0.3))
     hz = oracle.gauss_kernel("orc", ks, 1.0)
     base = rng.integers(0, 100, (h, stride)).astype(np.uint8)
     a = cvb.convlt1("8u32f8u", img, vt, hz, width=w, border=border, out=base.copy())
