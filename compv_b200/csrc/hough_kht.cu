@@ -691,6 +691,70 @@ __device__ int ksort_warp_partition(sse_item* a, int first, int last, IDX* Ls, I
 	return static_cast<int>(cl < cr ? cl : cr);
 }
 
+// The same partition step by the whole CTA, for the large ranges at the top of the recursion tree (the first three levels of a 5.7 k-cell frame are 1, 2 and 4 ranges:
+// one warp each would leave most of the CTA waiting at the level barrier).  Every warp scans a contiguous chunk; the two ordered lists are the concatenation of the
+// chunks' lists (L ascending: chunks in order; R descending: chunks in reverse order), so they are exactly the lists of ksort_warp_partition.
+#define KSORT_BIG 1024
+template <typename IDX>
+__device__ int ksort_block_partition(sse_item* a, int first, int last, IDX* Ls, IDX* Rs, int* sPart /* 24 ints of shared memory */)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned int lt = (1u << lane) - 1u;
+	if (tid == 0) sse_move_median_to_first(a, first, first + 1, first + (last - first) / 2, last - 1);
+	__syncthreads();
+	const unsigned int pk = sse_key(a[first]);
+	const int n = last - first - 1;
+	const int per = ((n + KSORT_WARPS * 32 - 1) / (KSORT_WARPS * 32)) * 32;
+	const int cb = min(first + 1 + warp * per, last), ce = min(cb + per, last); // my chunk of first+1 .. last-1
+	int cL = 0, cR = 0;
+	for (int base = cb; base < ce; base += 32) {
+		const int i = base + lane;
+		const bool in = i < ce;
+		const unsigned int k = in ? sse_key(a[i]) : 0u;
+		cL += __popc(__ballot_sync(0xffffffffu, in && !(k > pk)));
+		cR += __popc(__ballot_sync(0xffffffffu, in && !(pk > k)));
+	}
+	if (lane == 0) { sPart[warp] = cL; sPart[8 + warp] = cR; }
+	__syncthreads();
+	int offL = 0, offR = 0, nL = 0, nR = 0;
+	for (int w = 0; w < KSORT_WARPS; ++w) {
+		const int l_ = sPart[w], r_ = sPart[8 + w];
+		if (w < warp) offL += l_;
+		if (w > warp) offR += r_;
+		nL += l_; nR += r_;
+	}
+	int pos = offL;
+	for (int base = cb; base < ce; base += 32) {
+		const int i = base + lane;
+		const bool flag = i < ce && !(sse_key(a[i]) > pk);
+		const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+		if (flag) Ls[first + pos + __popc(bal & lt)] = static_cast<IDX>(i);
+		pos += __popc(bal);
+	}
+	pos = offR;
+	for (int base = ce - 1; base >= cb; base -= 32) {
+		const int i = base - lane;
+		const bool flag = i >= cb && !(pk > sse_key(a[i]));
+		const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+		if (flag) Rs[first + pos + __popc(bal & lt)] = static_cast<IDX>(i);
+		pos += __popc(bal);
+	}
+	__syncthreads();
+	const int m = nL < nR ? nL : nR;
+	int cnt = 0; // L ascends and R descends: L[k] < R[k] holds for k < K and for no other k
+	for (int k = tid; k < m; k += KSORT_THREADS) cnt += (static_cast<unsigned int>(Ls[first + k]) < static_cast<unsigned int>(Rs[first + k])) ? 1 : 0;
+	for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if (lane == 0) sPart[16 + warp] = cnt;
+	__syncthreads();
+	int K = 0;
+	for (int w = 0; w < KSORT_WARPS; ++w) K += sPart[16 + w];
+	for (int k = tid; k < K; k += KSORT_THREADS) { const unsigned int i = Ls[first + k], j = Rs[first + k]; const sse_item t = a[i]; a[i] = a[j]; a[j] = t; }
+	const unsigned int cl = (K < nL) ? static_cast<unsigned int>(Ls[first + K]) : 0xffffffffu;
+	const unsigned int cr = (K > 0) ? static_cast<unsigned int>(Rs[first + K - 1]) : static_cast<unsigned int>(last);
+	__syncthreads();
+	return static_cast<int>(cl < cr ? cl : cr);
+}
+
 __global__ void __launch_bounds__(KSORT_THREADS)
 kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict__ itemsAll, unsigned int* __restrict__ listsAll, int* __restrict__ rangesAll, int* __restrict__ accAll,
 	const double* __restrict__ rhoTab, const double* __restrict__ thetaTab, cvb200_hough_line_t* __restrict__ lines, unsigned long long capacity, unsigned long long* __restrict__ counts,
@@ -698,7 +762,7 @@ kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict
 {
 	extern __shared__ __align__(16) unsigned char ksortSmem[];
 	__shared__ unsigned int sWarp[9];
-	__shared__ int sCnt[2], sLeaves;
+	__shared__ int sCnt[2], sLeaves, sBigN, sBig[72][3], sPart[24];
 	const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (meta->overflow) { if (tid == 0) counts[frame] = 0; return; }
 	const KhtFrame& fr = frames[frame];
@@ -717,8 +781,32 @@ kht_peaks_sort_kernel(const KhtVote* __restrict__ votesAll, sse_item* __restrict
 		// level-synchronous evaluation of the recursion tree: ranges of one level are disjoint and independent
 		int* leaves = rangesAll + 2 * fr.voteOff;             // (first, last) pairs of ranges with 2..16 elements: at most nv / 2 of them
 		int* lvl[2] = { leaves + nv, leaves + nv + nv / 2 };   // (first, last, depth) triples of ranges > 16 elements: at most nv / 17 per level, room for nv / 6
-		if (tid == 0) { lvl[0][0] = 0; lvl[0][1] = nv; lvl[0][2] = sse_lg(static_cast<unsigned int>(nv)) * 2; sCnt[0] = 1; sCnt[1] = 0; sLeaves = 0; }
+		// phase 1: ranges above KSORT_BIG cells, one at a time by the whole CTA (a stack: at most one pending sibling per level of the depth limit)
+		if (tid == 0) { sBig[0][0] = 0; sBig[0][1] = nv; sBig[0][2] = sse_lg(static_cast<unsigned int>(nv)) * 2; sBigN = 1; sCnt[0] = 0; sCnt[1] = 0; sLeaves = 0; }
 		__syncthreads();
+		for (;;) {
+			const int nb = sBigN;
+			if (nb == 0) break;
+			const int f = sBig[nb - 1][0], l = sBig[nb - 1][1], d = sBig[nb - 1][2];
+			__syncthreads(); // everybody has read the top of the stack
+			int cut = -1;
+			if (l - f <= KSORT_BIG) { /* small from the start: straight to the level lists */ }
+			else if (d == 0) { if (tid == 0) sse_heap_sort(a + f, l - f); } // the depth-limit fallback of introsort
+			else cut = inSmem ? ksort_block_partition<unsigned short>(a, f, l, Ls16, Rs16, sPart) : ksort_block_partition<unsigned int>(a, f, l, Ls, Rs, sPart);
+			if (tid == 0) {
+				int top = nb - 1;
+				const int cf[2] = { cut >= 0 ? f : f, cut >= 0 ? cut : 0 }, cl[2] = { cut >= 0 ? cut : l, cut >= 0 ? l : 0 };
+				const int nChild = cut >= 0 ? 2 : ((l - f <= KSORT_BIG) ? 1 : 0), dc = cut >= 0 ? d - 1 : d;
+				for (int c = 0; c < nChild; ++c) {
+					const int len = cl[c] - cf[c];
+					if (len > KSORT_BIG && cut >= 0) { sBig[top][0] = cf[c]; sBig[top][1] = cl[c]; sBig[top][2] = dc; ++top; }
+					else if (len > SSE_THRESHOLD) { const int k = sCnt[0]++; lvl[0][3 * k] = cf[c]; lvl[0][3 * k + 1] = cl[c]; lvl[0][3 * k + 2] = dc; }
+					else if (len > 1) { const int k = sLeaves++; leaves[2 * k] = cf[c]; leaves[2 * k + 1] = cl[c]; }
+				}
+				sBigN = top;
+			}
+			__syncthreads();
+		}
 		for (int cur = 0;; cur ^= 1) {
 			const int cnt = sCnt[cur];
 			if (cnt == 0) break;
