@@ -5,7 +5,11 @@
 //     (cp.async.bulk.tensor.3d, out-of-image elements zero-filled by the hardware) -- no per-pixel load instructions;
 //   * every lane owns 4 consecutive pixels (one 32-bit shared-memory word per row): all shared-memory traffic is 32/64-bit and conflict free;
 //   * u8 <-> f32 conversions use the 2^23 magic-number trick (PRMT + FADD / FADD.RZ) instead of the quarter-rate I2F/F2I pipe;
-//   * gx/gy never reach shared memory: the gradient stage stores g (11 bits for Sobel 3x3) with the 2-bit NMS direction in bits 14-15.
+//   * the Gaussian runs on PACKED fp32 pairs (packed.cuh: fma.rn.f32x2 / add.rz.f32x2 = FFMA2 / FADD2 of sm_100a): each half rounds exactly like the scalar
+//     instruction, so the reference's FMA chain is reproduced bit for bit with half the issue slots (two rows per step horizontally, two columns vertically);
+//   * the Sobel stage works on two 16-bit pixels per 32-bit integer instruction (values biased so that no borrow crosses the halves);
+//   * gx/gy never reach shared memory: the gradient stage stores g (11 bits for Sobel 3x3); NMS candidates (g > tLow) are found by one ballot per pixel slot,
+//     kept one mask per lane and expanded once per warp into a queue that all 32 lanes work off (direction + the two neighbours only for candidates).
 // Tile geometry: a warp's 32 lanes x 4 px = 128 columns [x0-4, x0+124); blurred columns valid on [x0-2, x0+122), g on [x0-1, x0+121),
 // output on [x0, x0+120) (lanes 1..30).  120 divides 1920 and 3840, 60 divides 1080, 2160 and 480.
 #pragma once

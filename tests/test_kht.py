@@ -231,6 +231,28 @@ def test_cuda_canny_kht_device_pipeline_ring(cvb, sub, slots, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("sub,slots", [(4, 4), (7, 3), (5, 8)])
+def test_cuda_canny_kht_host_pipeline_ring_rotation(cvb, sub, slots, monkeypatch):
+    """cvb200_canny_kht_process_batch (host frames): the ring is rotated so that the LAST sub-batch runs on the last slot (the highest-priority stream), whatever the
+    number of sub-batches; slots are reused while earlier sub-batches are still in flight.  Every frame's lines must be the oracle's, in frame order."""
+    from compv_b200 import _ffi
+    monkeypatch.setenv("CVB200_PIPE_SUB", str(sub))
+    monkeypatch.setenv("CVB200_PIPE_SLOTS", str(slots))
+    w, h, batch = 320, 200, 23
+    frames = np.stack([frame_g(w, h, 1300 + k) if k % 3 else frame_text(w, h, k) for k in range(batch)])
+    canny = cvb.CompVEdgeDete.newObj(_ffi.CANNY_ID, 59.0, 119.0, 3)
+    canny.set_preblur(5, 1.0)
+    kht = cvb.CompVHough.newObj(_ffi.HOUGHKHT_ID, 1.0, 1.0, 30)
+    for _ in range(2):
+        got = cvb.canny_kht_process_batch(canny, kht, frames, width=w)
+        gs_last = None
+        for k in range(batch):
+            want, gs_last = oracle.hough_kht("orc", canny_edges(frames[k]), 1.0, 1.0, 30)
+            same_lines(got[k], want)
+        assert kht.getFloat64(_ffi.HOUGHKHT_GET_FLT64_GS) == gs_last
+
+
+@pytest.mark.gpu
 def test_cuda_kht_pools_grow_on_overflow(cvb):
     """The pools are sized from earlier calls: a first small call followed by a dense frame (every pool too small) must still give the oracle's lines."""
     from compv_b200 import _ffi
