@@ -427,22 +427,36 @@ sobel_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams p, 
 	}
 	constexpr int RPW = (CF_TH + CF_WARPS - 1) / CF_WARPS; // 8 output rows per warp
 	const int ro0 = warp * RPW;
-	int hs[3][4], hd[3][4]; // per source row: hs[i] = p[i-1] + 2p[i] + p[i+1], hd[i] = p[i+1] - p[i-1]
+	// Two pixels per 32-bit integer instruction, as in canny_front_fast_kernel: 16-bit halves hold pixels (0, 2) and (1, 3) of the lane's word, biased to stay non-negative.
+	unsigned int hs[3][2], hd[3][2]; // per source row: hs = p[i-1] + 2p[i] + p[i+1], hd = p[i+1] - p[i-1] + 256
 	const unsigned int* src = sA + woff + lane;
 	auto loadRow = [&](int rb, int slot) {
 		const unsigned int* sw = src + rb * CF_INW;
 		const unsigned int wl = sw[-1], wc = sw[0], wr = sw[1];
-		int q[6];
-		q[0] = static_cast<int>(wl >> 24);
-		q[1] = static_cast<int>(wc & 0xff); q[2] = static_cast<int>((wc >> 8) & 0xff); q[3] = static_cast<int>((wc >> 16) & 0xff); q[4] = static_cast<int>(wc >> 24);
-		q[5] = static_cast<int>(wr & 0xff);
-#pragma unroll
-		for (int i = 0; i < 4; ++i) { hs[slot][i] = q[i] + 2 * q[i + 1] + q[i + 2]; hd[slot][i] = q[i + 2] - q[i]; }
+		const unsigned int B = __byte_perm(wc, 0u, 0x4240);  // (p0, p2)
+		const unsigned int Cc = __byte_perm(wc, 0u, 0x4341); // (p1, p3)
+		const unsigned int A = __byte_perm(wl, Cc, 0x5453);  // (p-1, p1)
+		const unsigned int D = __byte_perm(B, wr, 0x1412);   // (p2, p4)
+		hs[slot][0] = A + 2u * B + Cc;
+		hs[slot][1] = B + 2u * Cc + D;
+		hd[slot][0] = Cc + 0x01000100u - A;
+		hd[slot][1] = D + 0x01000100u - B;
 	};
 	const bool laneOut = (lane >= 1 && lane <= 30);
-	unsigned int localMax = 0;
+	// the r = 1 border ring of the convolutions is zero: columns 1 <= x < W-1 of my four pixels as masks over the (0, 2) and (1, 3) pairs;
+	// pass 1 additionally looks only at the columns that count for the frame maximum (all of the image, or the x86 lanes of defect 1)
+	unsigned int cm[2] = { 0u, 0u }, mm[2] = { 0u, 0u };
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int x = xl + i;
+		if (x >= 1 && x < W - 1) cm[i & 1] |= 0xffffu << (16 * (i >> 1));
+		if (laneOut && x < W && (!gmaxLanes || ((0x17u >> (x & 7)) & 1u))) mm[i & 1] |= 0xffffu << (16 * (i >> 1));
+	}
+	unsigned int localMax2 = 0; // packed pair of running maxima
 	float scale = 0.f;
 	if (MODE == 3) scale = __fdiv_rn(255.f, static_cast<float>(max(gmaxIn[frame], 1u))); // scaleAndClip (compv_math_utils.cxx:336-364)
+	const f32x2 scale2 = pk2(__float_as_uint(scale), __float_as_uint(scale));
+	const f32x2 negMagic = pk2(0xCB000000u, 0xCB000000u), magic = pk2(0x4B000000u, 0x4B000000u);
 	uint8_t* __restrict__ cls = p.cls + frame * p.framePitch;
 	// output row y0 + ro reads staged rows ro + 1, ro + 2, ro + 3 (image rows y-1, y, y+1)
 	loadRow(ro0 + 1, 0);
@@ -454,33 +468,43 @@ sobel_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams p, 
 			loadRow(ro + 3, (j + 2) % 3);
 			const int a = j % 3, b = (j + 1) % 3, c = (j + 2) % 3;
 			const int y = y0 + ro;
-			const bool rowOk = (y >= 1 && y < H - 1);
-			unsigned int outw = 0;
+			unsigned int g[2] = { 0u, 0u };
+			if (y >= 1 && y < H - 1) {
 #pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				const int x = xl + i;
-				int gx = hd[a][i] + 2 * hd[b][i] + hd[c][i];
-				int gy = hs[c][i] - hs[a][i];
-				if (!(rowOk && x >= 1 && x < W - 1)) { gx = 0; gy = 0; } // the r = 1 border ring of the convolutions is zero
-				const unsigned int g = static_cast<unsigned int>(abs(gx) + abs(gy));
-				if (MODE == 2) {
-					if (laneOut && x < W && y < H && (!gmaxLanes || ((0x17u >> (x & 7)) & 1u))) localMax = max(localMax, g);
-				}
-				else {
-					const int v = __float2int_rz(__fmul_rn(static_cast<float>(g), scale));
-					outw |= static_cast<unsigned int>(min(max(v, 0), 255)) << (8 * i);
+				for (int h = 0; h < 2; ++h) {
+					const unsigned int gx = hd[a][h] + 2u * hd[b][h] + hd[c][h];    // gx + 1024 in [4, 2044]
+					const unsigned int gy = hs[c][h] + 0x04000400u - hs[a][h];      // gy + 1024
+					const unsigned int ax = __vmaxu2(gx, 0x08000800u - gx);         // |gx| + 1024
+					const unsigned int ay = __vmaxu2(gy, 0x08000800u - gy);
+					g[h] = (ax + ay - 0x08000800u) & cm[h];
 				}
 			}
-			if (MODE == 3 && laneOut && y < H && xl < W) {
-				uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
-				if (p.vecStore && xl + 4 <= W) *reinterpret_cast<unsigned int*>(o) = outw;
-				else {
+			if (MODE == 2) {
+				if (y < H) localMax2 = __vmaxu2(localMax2, __vmaxu2(g[0] & mm[0], g[1] & mm[1]));
+			}
+			else {
+				// u8(trunc(g * scale)) clamped to 255: (float)g by the 2^23 trick (g <= 2040), the product is < 2^23, adding 2^23 toward zero leaves trunc() in the low mantissa bits
+				unsigned int v[4];
 #pragma unroll
-					for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+				for (int h = 0; h < 2; ++h) {
+					const f32x2 gf = fadd2(pk2(__byte_perm(g[h], 0x4B000000u, 0x7410), __byte_perm(g[h], 0x4B000000u, 0x7432)), negMagic); // pixels h and h + 2
+					unsigned int lo, hi;
+					unpk2(fadd2_rz(fmul2(gf, scale2), magic), lo, hi);
+					v[h] = min(lo & 0x7fffffu, 255u); v[h + 2] = min(hi & 0x7fffffu, 255u);
+				}
+				const unsigned int outw = pack4(v[0], v[1], v[2], v[3]);
+				if (laneOut && y < H && xl < W) {
+					uint8_t* o = cls + static_cast<size_t>(y) * p.stride + xl;
+					if (p.vecStore && xl + 4 <= W) *reinterpret_cast<unsigned int*>(o) = outw;
+					else {
+#pragma unroll
+						for (int i = 0; i < 4; ++i) if (xl + i < W) o[i] = static_cast<uint8_t>(outw >> (8 * i));
+					}
 				}
 			}
 		}
 	}
+	unsigned int localMax = max(localMax2 & 0xffffu, localMax2 >> 16);
 	if (MODE == 2) {
 		for (int o = 16; o; o >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
 		if (lane == 0 && localMax) atomicMax(&gmaxOut[frame], localMax);
