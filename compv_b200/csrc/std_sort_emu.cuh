@@ -139,4 +139,31 @@ SSE_FN int sse_partition_closed_form(sse_item* a, int first, int last, unsigned 
 	const unsigned int cr = (K > 0) ? Rs[K - 1] : static_cast<unsigned int>(last);
 	return static_cast<int>(cl < cr ? cl : cr);
 }
+
+// The same step as the CTA-wide device code builds it (ksort_block_partition in hough_kht.cu): `chunks` workers scan contiguous chunks of first+1 .. last-1 whose size is a
+// multiple of 32; L is the chunks' ascending lists in chunk order, R the chunks' descending lists in REVERSE chunk order; K is the NUMBER of k < min(nL, nR) with
+// L[k] < R[k] (L ascends and R descends, so the predicate is monotone and the count equals the first failing index).  Serial statement for the CPU check.
+SSE_FN int sse_partition_closed_form_chunked(sse_item* a, int first, int last, unsigned int* Ls, unsigned int* Rs, int chunks)
+{
+	sse_move_median_to_first(a, first, first + 1, first + (last - first) / 2, last - 1);
+	const sse_item pivot = a[first];
+	const int n = last - first - 1;
+	const int per = ((n + chunks * 32 - 1) / (chunks * 32)) * 32;
+	int nL = 0, nR = 0;
+	for (int w = 0; w < chunks; ++w) { // L: chunk order
+		const int cb = (first + 1 + w * per < last) ? first + 1 + w * per : last, ce = (cb + per < last) ? cb + per : last;
+		for (int i = cb; i < ce; ++i) if (!sse_less(a[i], pivot)) Ls[nL++] = static_cast<unsigned int>(i);
+	}
+	for (int w = chunks - 1; w >= 0; --w) { // R: reverse chunk order, descending inside a chunk
+		const int cb = (first + 1 + w * per < last) ? first + 1 + w * per : last, ce = (cb + per < last) ? cb + per : last;
+		for (int i = ce - 1; i >= cb; --i) if (!sse_less(pivot, a[i])) Rs[nR++] = static_cast<unsigned int>(i);
+	}
+	const int m = nL < nR ? nL : nR;
+	int K = 0;
+	for (int k = 0; k < m; ++k) K += (Ls[k] < Rs[k]) ? 1 : 0;
+	for (int k = 0; k < K; ++k) { const sse_item t = a[Ls[k]]; a[Ls[k]] = a[Rs[k]]; a[Rs[k]] = t; }
+	const unsigned int cl = (K < nL) ? Ls[K] : 0xffffffffu;
+	const unsigned int cr = (K > 0) ? Rs[K - 1] : static_cast<unsigned int>(last);
+	return static_cast<int>(cl < cr ? cl : cr);
+}
 } // namespace cvb

@@ -12,7 +12,7 @@ using namespace cvb;
 static unsigned int lcg(unsigned int& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 
 // the recursion tree evaluated breadth first with the closed-form partition (any order is allowed: ranges are disjoint)
-static void sort_closed_form(std::vector<sse_item>& a, int depth0, bool reverseOrder)
+static void sort_closed_form(std::vector<sse_item>& a, int depth0, bool reverseOrder, int bigChunks = 0)
 {
 	struct R { int f, l, d; };
 	std::vector<R> work, next;
@@ -26,7 +26,9 @@ static void sort_closed_form(std::vector<sse_item>& a, int depth0, bool reverseO
 		for (const R& r : work) {
 			if (r.l - r.f <= SSE_THRESHOLD) { sse_insertion_sort(a.data(), r.f, r.l); continue; }
 			if (r.d == 0) { sse_heap_sort(a.data() + r.f, r.l - r.f); continue; }
-			const int cut = sse_partition_closed_form(a.data(), r.f, r.l, Ls.data() + r.f, Rs.data() + r.f);
+			// ranges above 1024 elements: the CTA-wide formulation (8 chunks), as the device code does (KSORT_BIG)
+			const int cut = (bigChunks && r.l - r.f > 1024) ? sse_partition_closed_form_chunked(a.data(), r.f, r.l, Ls.data() + r.f, Rs.data() + r.f, bigChunks)
+			                                                  : sse_partition_closed_form(a.data(), r.f, r.l, Ls.data() + r.f, Rs.data() + r.f);
 			next.push_back({ r.f, cut, r.d - 1 });
 			next.push_back({ cut, r.l, r.d - 1 });
 		}
@@ -61,7 +63,9 @@ int main(int argc, char** argv)
 		std::vector<sse_item> g1 = in; sse_sort_serial(g1.data(), n);
 		std::vector<sse_item> g2 = in; sort_closed_form(g2, n > 1 ? sse_lg(n) * 2 : 0, false);
 		std::vector<sse_item> g3 = in; sort_closed_form(g3, n > 1 ? sse_lg(n) * 2 : 0, true);
-		if (g1 != want || g2 != want || g3 != want) { ++bad; fprintf(stderr, "MISMATCH std::sort n=%d kind=%d (%d %d %d)\n", n, kind, g1 != want, g2 != want, g3 != want); }
+		std::vector<sse_item> g4 = in; sort_closed_form(g4, n > 1 ? sse_lg(n) * 2 : 0, false, 8);
+		std::vector<sse_item> g5 = in; sort_closed_form(g5, n > 1 ? sse_lg(n) * 2 : 0, true, 3);
+		if (g1 != want || g2 != want || g3 != want || g4 != want || g5 != want) { ++bad; fprintf(stderr, "MISMATCH std::sort n=%d kind=%d (%d %d %d %d %d)\n", n, kind, g1 != want, g2 != want, g3 != want, g4 != want, g5 != want); }
 		// shallow depth limits force the heap-sort fallback: compare with libstdc++'s own loop run with the same limit
 		for (int d = 0; d <= 3 && n > 1; ++d) {
 			std::vector<sse_item> w2 = in;
@@ -69,6 +73,8 @@ int main(int argc, char** argv)
 			std::__final_insertion_sort(w2.begin(), w2.end(), __gnu_cxx::__ops::__iter_comp_iter(comp));
 			std::vector<sse_item> h1 = in; sse_sort_range_serial(h1.data(), 0, n, d);
 			std::vector<sse_item> h2 = in; sort_closed_form(h2, d, false);
+			std::vector<sse_item> h3 = in; sort_closed_form(h3, d, false, 8);
+			if (h3 != w2) { ++bad; fprintf(stderr, "MISMATCH depth-limited chunked n=%d kind=%d d=%d\n", n, kind, d); }
 			if (h1 != w2 || h2 != w2) { ++bad; fprintf(stderr, "MISMATCH depth-limited n=%d kind=%d d=%d (%d %d)\n", n, kind, d, h1 != w2, h2 != w2); }
 		}
 	}
