@@ -93,6 +93,15 @@ def make_frames(n, seed0):
     return np.stack([frame_g(W, H, seed0 + k) for k in range(n)])
 
 
+def tile_frames(dst, base):
+    """dst[k] = base[k % len(base)] for every frame of dst (the synthetic batch cycles a few dozen distinct frames); returns dst."""
+    n = len(base)
+    for s0 in range(0, len(dst), n):
+        m = min(n, len(dst) - s0)
+        dst[s0:s0 + m] = base[:m]
+    return dst
+
+
 def run_reference(args, rank, world):
     """--impl reference: the unmodified reference (oracle/_ref) on the host cores; rank 0 only."""
     if rank != 0:
@@ -361,10 +370,16 @@ def main():
 
     B = args.frames
     distinct = min(B, 64)
-    frames = np.concatenate([make_frames(distinct, shard.weak_seed(12345, rank))] * ((B + distinct - 1) // distinct))[:B]  # (B, H, W) uint8: larger than the 126 MB L2
-    h_in = torch.from_numpy(frames).pin_memory()
+    base = make_frames(distinct, shard.weak_seed(12345, rank))
+    try:  # the batch (B, H, W) uint8 -- larger than the 126 MB L2 -- is tiled straight into pinned memory: no pageable copy of the 8.5 GB beside it
+        h_in = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+        tile_frames(h_in.numpy(), base)
+        host_batch = "tiled into pinned memory"
+    except Exception:
+        h_in = torch.from_numpy(tile_frames(np.empty((B, H, W), np.uint8), base)).pin_memory()
+        host_batch = "pageable array copied into pinned memory"
     d_in = h_in.cuda()
-    frames = frames[:8].copy()  # the CPU baseline below cycles 8 frames; the full batch now lives in the pinned buffer and on the device
+    frames = base[:8].copy()  # the CPU baseline below cycles 8 frames
     dete = cvb.CompVEdgeDete.newObj(cvb.CANNY_ID, TLOW, THIGH, KS)
     dete.set_preblur(BLUR, SIGMA)
     kht = cvb.CompVHough.newObj(cvb.HOUGHKHT_ID, 1.0, 1.0, KHT_THRESHOLD)
@@ -514,7 +529,7 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int16 (+f32 blur)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "frames_per_gpu_per_step": B, "tLow": TLOW, "tHigh": THIGH,
-                       "kernSize": KS, "blur": [BLUR, SIGMA], "kht": {"rho": 1, "theta_deg": 1, "threshold": KHT_THRESHOLD}, "lines_per_step_per_rank": lines_all, "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6),
+                       "kernSize": KS, "blur": [BLUR, SIGMA], "kht": {"rho": 1, "theta_deg": 1, "threshold": KHT_THRESHOLD}, "lines_per_step_per_rank": lines_all, "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (B * W * H / 1e6), "host_batch": host_batch,
                        "parallelism": "frames sharded across %d GPU(s), no collective" % world},
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": B * W * H * world, "d2h_bytes_per_step": sum(lines_all) * 16,
                     "ms_per_step": e2e_ms / args.steps, "api": "cvb200_canny_kht_process_batch (pinned host frames in, lines out)"},
